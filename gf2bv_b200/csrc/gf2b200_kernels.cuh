@@ -1,0 +1,657 @@
+/*
+ * gf2b200_kernels.cuh -- sm_100a kernels of the B200 GF(2) solver.
+ *
+ * What this replaces in the reference: the M4RI calls behind
+ * gf2bv/_internal.c:433 (_mzd_pluq), :440 (_mzd_pluq_solve_left) and :343
+ * (mzd_trsm_upper_left inside _mzd_kernel_left_pluq, :309-357).  The algorithm
+ * is NOT M4RI's recursive PLE; it is a right-looking blocked elimination with
+ * 64-column panels designed around HBM streaming:
+ *
+ *   HBM layout ("strip-major"): the augmented matrix [A | b] is cut into column
+ *   strips of 8 words (64 B).  Strip s holds, for every row i, the 64-byte piece
+ *   words 8s..8s+7 of that row, rows contiguous:  word(i, w) lives at
+ *       base[((w / 8) * mp + i) * 8 + (w % 8)].
+ *   A sweep work unit (one strip x 1024 rows) is therefore ONE contiguous 64 KiB
+ *   region: perfectly coalesced 128-bit loads/stores, no strided DRAM pages.
+ *   b sits alone in word nw (bit 0).
+ *
+ *   per panel (word column w):
+ *     k_select  one CTA: XOR-basis insertion over the dense panel-column array
+ *               pc[] (warp ballot picks the next pivot row, warp shuffle
+ *               broadcasts its 64-bit pivot word); yields <= 64 pivot rows, the
+ *               pivot-column mask (= the panel's column rank profile) and the
+ *               64x64 transform TB that turns the selected rows into RREF.
+ *     k_apply   per strip: E = TB * Sel (reduced pivot rows), stores them at rows
+ *               r..r+k-1 (physical swap with the displaced rows) and into the
+ *               L2-resident staging tile ebuf[s] (64 x 64 B, indexed by column).
+ *     k_sweep   persistent, 1 CTA / SM: TMA bulk-copies ebuf[s] into shared
+ *               memory, builds eight 256-entry Four-Russians tables (128 KiB),
+ *               then streams every active row piece: 8 table XORs per 16 B.
+ *               This is the HBM-bound kernel (2 * rows * 64 B per strip).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gf2b200 {
+
+typedef unsigned long long u64;
+
+#define GF2_PHI 0x9E3779B97F4A7C15ULL
+
+struct Mat {
+	u64 *base;      /* strip-major storage, ns * mp * 8 words */
+	long long mp;   /* padded row count (multiple of 16) */
+	long long m;    /* rows held here */
+	long long n;    /* unknowns */
+	int nw;         /* ceil(n / 64): A words per row */
+	int ns;         /* strips: ceil((nw + 1) / 8) */
+};
+
+/* Device-resident description of the current panel (written by k_select). */
+struct PanelDesc {
+	long long r;     /* echelon rows before this panel */
+	int k;           /* pivots found in this panel */
+	int nmove;       /* displaced rows to relocate */
+	u64 pm;          /* pivot column mask within the panel word */
+	u64 TB[64];      /* by column c: combination of selected rows giving E_c; 0 if c is free */
+	int sel[64];     /* physical row of the l-th selected row */
+	int mv_src[64];
+	int mv_dst[64];
+};
+
+struct SolverState {
+	long long r;     /* current rank == first active row */
+	int inconsistent;
+	int pad;
+};
+
+__host__ __device__ __forceinline__ u64 mix64(u64 z) {
+	z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
+	z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+	z ^= z >> 31;
+	return z;
+}
+
+__device__ __forceinline__ long long widx(const Mat &M, long long i, int w) {
+	return ((long long)(w >> 3) * M.mp + i) * 8 + (w & 7);
+}
+
+__device__ __forceinline__ u64 shfl64(u64 v, int src) {
+	unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
+	unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+	return ((u64)hi << 32) | lo;
+}
+
+/* ------------------------------------------------------------------------
+ * Loading: row-major words -> strip-major, masking bits >= n (the reference
+ * ignores them, _internal.c:45,48) and placing b (bit i of the packed b) in
+ * word nw.  One thread per (row, word); 8 consecutive lanes write one 64 B piece.
+ * ---------------------------------------------------------------------- */
+__global__ void k_layout(Mat M, const u64 *__restrict__ src, const u64 *__restrict__ bsrc,
+                         long long stride, long long row0, long long nrows, long long brow0) {
+	const int WT = M.ns * 8;
+	long long total = nrows * WT;
+	for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+	     t += (long long)gridDim.x * blockDim.x) {
+		long long il = t / WT;
+		int w = (int)(t - il * WT);
+		u64 v = 0;
+		if (w < M.nw) {
+			v = src[il * stride + w];
+			if (w == M.nw - 1 && (M.n & 63)) v &= (1ULL << (M.n & 63)) - 1;
+		} else if (w == M.nw && bsrc) {
+			long long bi = brow0 + il;
+			v = (bsrc[bi >> 6] >> (bi & 63)) & 1;
+		}
+		M.base[widx(M, row0 + il, w)] = v;
+	}
+}
+
+/* Synthetic dense system of SURVEY.md 8(d): word(i, w) = mix(seed + PHI*(i*nw + w + 1)),
+ * i = GLOBAL row index (grow0 + local). */
+__global__ void k_generate(Mat M, u64 seed, long long grow0) {
+	const int WT = M.ns * 8;
+	long long total = M.m * WT;
+	for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+	     t += (long long)gridDim.x * blockDim.x) {
+		long long il = t / WT;
+		int w = (int)(t - il * WT);
+		u64 v = 0;
+		if (w < M.nw) {
+			v = mix64(seed + GF2_PHI * (u64)((grow0 + il) * M.nw + w + 1));
+			if (w == M.nw - 1 && (M.n & 63)) v &= (1ULL << (M.n & 63)) - 1;
+		}
+		M.base[widx(M, il, w)] = v;
+	}
+}
+
+/* parity(<A_i, vec>) with A regenerated from the seed (no matrix reads).
+ * mode 0: write it as b into word nw of row i.  mode 1: count rows where it is 1.
+ * One warp per row. */
+__global__ void k_synth_dot(Mat M, u64 seed, long long grow0, const u64 *__restrict__ vec,
+                            int mode, unsigned long long *count) {
+	int lane = threadIdx.x & 31;
+	long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+	long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+	for (long long il = warp; il < M.m; il += nwarps) {
+		u64 acc = 0;
+		for (int w = lane; w < M.nw; w += 32) {
+			u64 v = mix64(seed + GF2_PHI * (u64)((grow0 + il) * M.nw + w + 1));
+			if (w == M.nw - 1 && (M.n & 63)) v &= (1ULL << (M.n & 63)) - 1;
+			acc ^= v & vec[w];
+		}
+		int p = __popcll(acc) & 1;
+		p = __reduce_xor_sync(0xffffffffu, p);
+		if (lane == 0) {
+			if (mode == 0) M.base[widx(M, il, M.nw)] = (u64)p;
+			else if (p) atomicAdd(count, 1ULL);
+		}
+	}
+}
+
+/* x* of the synthetic system: nw words from the generator with seed ^ 0xB200 */
+__global__ void k_synth_xstar(u64 *x, int nw, long long n, u64 seed) {
+	int w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= nw) return;
+	u64 v = mix64((seed ^ 0xB200ULL) + GF2_PHI * (u64)(w + 1));
+	if (w == nw - 1 && (n & 63)) v &= (1ULL << (n & 63)) - 1;
+	x[w] = v;
+}
+
+__global__ void k_xor_vec(u64 *dst, const u64 *a, const u64 *b, int nw) {
+	int w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w < nw) dst[w] = a[w] ^ b[w];
+}
+
+/* dense copy of word column w for rows [row0, m) */
+__global__ void k_extract_pc(Mat M, int w, u64 *__restrict__ pc, long long row0) {
+	for (long long i = row0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M.m;
+	     i += (long long)gridDim.x * blockDim.x)
+		pc[i] = M.base[widx(M, i, w)];
+}
+
+/* ------------------------------------------------------------------------
+ * k_select: pivot search for panel word w over the active rows [r, m).
+ *
+ * Maintains an RREF XOR-basis B[c] (keyed by lowest set bit = leftmost column)
+ * of the 64-bit panel slices seen so far; TB[c] records which selected rows were
+ * XORed to form B[c].  The set of keys after all active rows are absorbed is the
+ * panel's column rank profile (an invariant of the row space), which is what
+ * _mzd_pluq's Q reports (_internal.c:433).  Stops early once every
+ * valid column of the panel is a pivot.
+ *
+ * All 32 warps reduce 1024 rows against the basis snapshot and compact the
+ * survivors; warp 0 then inserts them one at a time: __ballot_sync finds the
+ * next candidate lane, __shfl_sync broadcasts its pivot word.
+ * ---------------------------------------------------------------------- */
+#define SEL_THREADS 1024
+
+__device__ __forceinline__ void warp0_insert(u64 *B, u64 *TB, int *sel, u64 &pm, int &nsel,
+                                             const u64 colmask, u64 v, u64 tv, int row, int lane) {
+	/* re-reduce against pivots added since the snapshot (B is RREF: one shot) */
+	u64 x = v & pm;
+	while (x) {
+		int c = __ffsll((long long)x) - 1;
+		x &= x - 1;
+		v ^= B[c];
+		tv ^= TB[c];
+	}
+	__syncwarp();
+	while (pm != colmask) {
+		unsigned bal = __ballot_sync(0xffffffffu, v != 0);
+		if (!bal) break;
+		int src = __ffs((int)bal) - 1;
+		u64 u = shfl64(v, src);
+		u64 tu = shfl64(tv, src);
+		int urow = __shfl_sync(0xffffffffu, row, src);
+		int c = __ffsll((long long)u) - 1;
+		tu ^= 1ULL << nsel;
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			int cc = lane + 32 * h;
+			if ((pm >> cc) & 1) {
+				u64 b = B[cc];
+				if ((b >> c) & 1) {
+					B[cc] = b ^ u;
+					TB[cc] ^= tu;
+				}
+			}
+		}
+		if (lane == 0) {
+			B[c] = u;
+			TB[c] = tu;
+			sel[nsel] = urow;
+		}
+		pm |= 1ULL << c;
+		nsel++;
+		if ((v >> c) & 1) {
+			v ^= u;
+			tv ^= tu;
+		}
+		__syncwarp();
+	}
+}
+
+/* Shared scan body: absorbs rows [r, m) of pc into the basis.  Returns via smem. */
+struct SelectSmem {
+	u64 B[64], TB[64];
+	u64 qv[SEL_THREADS], qtv[SEL_THREADS];
+	int qrow[SEL_THREADS];
+	int sel[64];
+	int topsel[64];
+	int mv_src[64], mv_dst[64];
+	int wcount[32];
+	u64 pm;
+	int nsel;
+};
+
+__device__ __forceinline__ void select_scan(SelectSmem &S, const u64 *__restrict__ pc, long long r,
+                                            long long m, u64 colmask) {
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	for (long long base = r; base < m; base += SEL_THREADS) {
+		u64 pm = S.pm;
+		if (pm == colmask) break;
+		long long i = base + tid;
+		u64 v = (i < m) ? (pc[i] & colmask) : 0;
+		u64 tv = 0;
+		u64 x = v & pm;
+		while (x) {
+			int c = __ffsll((long long)x) - 1;
+			x &= x - 1;
+			v ^= S.B[c];
+			tv ^= S.TB[c];
+		}
+		unsigned bal = __ballot_sync(0xffffffffu, v != 0);
+		if (lane == 0) S.wcount[warp] = __popc(bal);
+		__syncthreads();
+		int off = 0, total = 0;
+#pragma unroll
+		for (int q = 0; q < 32; q++) {
+			int cnt = S.wcount[q];
+			if (q < warp) off += cnt;
+			total += cnt;
+		}
+		if (v) {
+			int pos = off + __popc(bal & ((1u << lane) - 1));
+			S.qv[pos] = v;
+			S.qtv[pos] = tv;
+			S.qrow[pos] = (int)i;
+		}
+		__syncthreads();
+		if (warp == 0) {
+			int nsel = S.nsel;
+			for (int q0 = 0; q0 < total && pm != colmask; q0 += 32) {
+				int q = q0 + lane;
+				u64 cv = (q < total) ? S.qv[q] : 0;
+				u64 ctv = (q < total) ? S.qtv[q] : 0;
+				int crow = (q < total) ? S.qrow[q] : -1;
+				warp0_insert(S.B, S.TB, S.sel, pm, nsel, colmask, cv, ctv, crow, lane);
+			}
+			if (lane == 0) {
+				S.pm = pm;
+				S.nsel = nsel;
+			}
+		}
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(SEL_THREADS, 1)
+k_select(Mat M, u64 *__restrict__ pc, int w, u64 colmask, SolverState *st, PanelDesc *pd,
+         long long *hist_r, u64 *hist_pm) {
+	__shared__ SelectSmem S;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const long long r = st->r, m = M.m;
+	if (tid < 64) {
+		S.B[tid] = 0;
+		S.TB[tid] = 0;
+		S.sel[tid] = -1;
+		S.topsel[tid] = 0;
+	}
+	if (tid == 0) {
+		S.pm = 0;
+		S.nsel = 0;
+	}
+	__syncthreads();
+	select_scan(S, pc, r, m, colmask);
+	if (warp != 0) return;
+	/* ---- finalise (warp 0) ---- */
+	const u64 pm = S.pm;
+	const int k = S.nsel;
+	for (int c = lane; c < 64; c += 32) {
+		pd->TB[c] = ((pm >> c) & 1) ? S.TB[c] : 0;
+		pd->sel[c] = S.sel[c];
+	}
+	/* rows r..r+k-1 become the echelon rows; selected rows already there stay,
+	 * the others ("displaced") move to the positions vacated by selected rows */
+	for (int l = lane; l < k; l += 32) {
+		int srow = S.sel[l];
+		if (srow < r + k) S.topsel[srow - (int)r] = 1;
+	}
+	__syncwarp();
+	int nvac = 0, ndis = 0;
+	for (int h = 0; h < 2; h++) {
+		int l = lane + 32 * h;
+		bool vac = (l < k) && (S.sel[l] >= r + k);
+		unsigned bv = __ballot_sync(0xffffffffu, vac);
+		if (vac) S.mv_dst[nvac + __popc(bv & ((1u << lane) - 1))] = S.sel[l];
+		nvac += __popc(bv);
+		bool dis = (l < k) && !S.topsel[l];
+		unsigned bd = __ballot_sync(0xffffffffu, dis);
+		if (dis) S.mv_src[ndis + __popc(bd & ((1u << lane) - 1))] = (int)r + l;
+		ndis += __popc(bd);
+	}
+	__syncwarp();
+	/* keep the dense panel column consistent with the row moves */
+	u64 tmpv[2];
+	for (int h = 0; h < 2; h++) {
+		int q = lane + 32 * h;
+		tmpv[h] = (q < ndis) ? pc[S.mv_src[q]] : 0;
+	}
+	__syncwarp();
+	for (int h = 0; h < 2; h++) {
+		int q = lane + 32 * h;
+		if (q < ndis) {
+			pc[S.mv_dst[q]] = tmpv[h];
+			pd->mv_src[q] = S.mv_src[q];
+			pd->mv_dst[q] = S.mv_dst[q];
+		}
+	}
+	if (lane == 0) {
+		pd->r = r;
+		pd->k = k;
+		pd->nmove = ndis;
+		pd->pm = pm;
+		st->r = r + k;
+		hist_r[w] = r;
+		hist_pm[w] = pm;
+	}
+}
+
+/* ------------------------------------------------------------------------
+ * k_apply: per strip s >= s0: E_c = XOR_{l in TB[c]} Sel_l for every pivot column
+ * c, stored (a) at matrix row r + rank(c) and (b) in ebuf[s][c] (zero rows for
+ * free columns) for the sweep's TMA load; displaced rows go to the vacated
+ * positions.  256 threads = 64 rows x 4 x 16 B.
+ * `selsrc` != nullptr: selected rows come from a gathered buffer [ns][64][64 B]
+ * (multi-GPU, after the pivot-row exchange) instead of the local matrix.
+ * ---------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256)
+k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s0) {
+	__shared__ uint4 Sel[64][4];
+	__shared__ uint4 Dis[64][4];
+	__shared__ u64 sTB[64];
+	__shared__ int ssel[64], ssrc[64], sdst[64];
+	const int k = pd->k;
+	if (k == 0) return;
+	const int tid = threadIdx.x, rr = tid >> 2, ch = tid & 3;
+	const long long r = pd->r;
+	const int nmove = pd->nmove;
+	const u64 pm = pd->pm;
+	if (tid < 64) {
+		sTB[tid] = pd->TB[tid];
+		ssel[tid] = pd->sel[tid];
+		ssrc[tid] = pd->mv_src[tid];
+		sdst[tid] = pd->mv_dst[tid];
+	}
+	__syncthreads();
+	uint4 *mb = reinterpret_cast<uint4 *>(M.base);
+	const int erow = (int)r + __popcll(pm & ((1ULL << rr) - 1));
+	const bool ispiv = (pm >> rr) & 1;
+	for (int s = s0 + blockIdx.x; s < M.ns; s += gridDim.x) {
+		const long long sb = (long long)s * M.mp;
+		uint4 z = make_uint4(0, 0, 0, 0);
+		Sel[rr][ch] = (rr < k) ? mb[(sb + ssel[rr]) * 4 + ch] : z;
+		if (rr < nmove) Dis[rr][ch] = mb[(sb + ssrc[rr]) * 4 + ch];
+		__syncthreads();
+		uint4 acc = z;
+		u64 t = sTB[rr];
+		while (t) {
+			int l = __ffsll((long long)t) - 1;
+			t &= t - 1;
+			uint4 v = Sel[l][ch];
+			acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+		}
+		ebuf[(long long)s * 256 + rr * 4 + ch] = acc;
+		if (ispiv) mb[(sb + erow) * 4 + ch] = acc;
+		if (rr < nmove) mb[(sb + sdst[rr]) * 4 + ch] = Dis[rr][ch];
+		__syncthreads();
+	}
+}
+
+/* ------------------------------------------------------------------------
+ * k_sweep: the HBM-bound row-XOR sweep.
+ *   rows [r1, m) x strips [s0, ns):  piece ^= XOR_g T[g][byte g of (pc_cur[row] & pm)]
+ * Persistent grid (1 CTA of 1024 threads per SM); work units of 1024 rows x one
+ * strip are dealt out contiguously in strip-major order so a CTA rebuilds its
+ * tables only when it crosses into a new strip.
+ * Shared memory: T[8][256][4] uint4 (128 KiB) | T4[8][2][16][4] (16 KiB) |
+ * E[64][4] (4 KiB, filled by cp.async.bulk + mbarrier) | mbarrier.
+ * The CTA that updates the strip holding word w+1 also emits the dense copy of
+ * that word column (pc_next) for the next panel's pivot search.
+ * ---------------------------------------------------------------------- */
+#define SWEEP_THREADS 1024
+#define SWEEP_U 4
+#define SWEEP_RU (SWEEP_THREADS / 4 * SWEEP_U) /* rows per unit */
+#define SWEEP_SMEM (8 * 256 * 4 * 16 + 8 * 2 * 16 * 4 * 16 + 64 * 4 * 16 + 16)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+	return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+	             "r"(bytes)
+	             : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned phase) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "W_%=:\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+	    "@!p bra W_%=;\n\t}" ::"r"(smem_u32(bar)),
+	    "r"(phase)
+	    : "memory");
+}
+/* 1-D TMA: global -> shared bulk copy completing on an mbarrier (SASS: UBLKCP) */
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar) {
+	asm volatile(
+	    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+	        smem_u32(dst)),
+	    "l"(src), "r"(bytes), "r"(smem_u32(bar))
+	    : "memory");
+}
+
+__device__ __forceinline__ void xor4(uint4 &a, const uint4 &b) {
+	a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w;
+}
+
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
+        u64 *__restrict__ pc_next, const uint4 *__restrict__ ebuf, int w, int s0) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	uint4 *T = reinterpret_cast<uint4 *>(smem_raw);
+	uint4 *T4 = T + 8 * 256 * 4;
+	uint4 *E = T4 + 8 * 2 * 16 * 4;
+	u64 *bar = reinterpret_cast<u64 *>(E + 64 * 4);
+
+	const int tid = threadIdx.x;
+	const int k = pd->k;
+	const long long r1 = pd->r + k;
+	const long long m = M.m;
+	if (r1 >= m) return;
+	const int wn = w + 1; /* next panel word (or the b word): always exists */
+	const int snext = wn >> 3;
+	if (k == 0) {
+		/* nothing to eliminate: only hand the next word column to k_select */
+		for (long long i = r1 + blockIdx.x * (long long)SWEEP_THREADS + tid; i < m;
+		     i += (long long)gridDim.x * SWEEP_THREADS)
+			pc_next[i] = M.base[widx(M, i, wn)];
+		return;
+	}
+	const u64 pm = pd->pm;
+	const long long rows = m - r1;
+	const long long nchunks = (rows + SWEEP_RU - 1) / SWEEP_RU;
+	const long long units = (long long)(M.ns - s0) * nchunks;
+	const long long u0 = units * blockIdx.x / gridDim.x;
+	const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
+	if (u0 >= u1) return;
+	if (tid == 0) {
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	unsigned phase = 0;
+	int cur = -1;
+	const int ch = tid & 3, rl = tid >> 2;
+	const int nch = (wn & 7) >> 1; /* chunk holding word wn inside its strip */
+	uint4 *mb = reinterpret_cast<uint4 *>(M.base);
+	const uint4 *Tc = T + ch;
+
+	for (long long u = u0; u < u1; ++u) {
+		const int s = s0 + (int)(u / nchunks);
+		const long long chunk = u % nchunks;
+		if (s != cur) {
+			__syncthreads(); /* everyone is done with the previous tables */
+			if (tid == 0) {
+				mbar_expect_tx(bar, 4096);
+				tma_bulk_g2s(E, ebuf + (long long)s * 256, 4096, bar);
+			}
+			mbar_wait(bar, phase);
+			phase ^= 1;
+			{ /* 16-entry half tables: tid = ((g*2+h)*16+e)*4+ch */
+				const int gh = tid >> 6, e = (tid >> 2) & 15;
+				uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll
+				for (int b = 0; b < 4; b++)
+					if ((e >> b) & 1) xor4(acc, E[(gh * 4 + b) * 4 + ch]);
+				T4[tid] = acc;
+			}
+			__syncthreads();
+			{
+				const int idx = tid >> 2;
+#pragma unroll
+				for (int g = 0; g < 8; g++) {
+					uint4 a = T4[((g * 2 + 0) * 16 + (idx & 15)) * 4 + ch];
+					uint4 b = T4[((g * 2 + 1) * 16 + (idx >> 4)) * 4 + ch];
+					xor4(a, b);
+					T[(g * 256 + idx) * 4 + ch] = a;
+				}
+			}
+			__syncthreads();
+			cur = s;
+		}
+		const long long row0 = r1 + chunk * SWEEP_RU + rl;
+		const bool force = (s == snext);
+		uint4 *p = mb + ((long long)s * M.mp + row0) * 4 + ch;
+		u64 cf[SWEEP_U];
+		uint4 d[SWEEP_U];
+		bool act[SWEEP_U];
+#pragma unroll
+		for (int q = 0; q < SWEEP_U; q++) {
+			long long row = row0 + (SWEEP_THREADS / 4) * q;
+			cf[q] = (row < m) ? (__ldg(pc_cur + row) & pm) : 0;
+		}
+#pragma unroll
+		for (int q = 0; q < SWEEP_U; q++) {
+			long long row = row0 + (SWEEP_THREADS / 4) * q;
+			act[q] = (row < m) && (cf[q] != 0 || force);
+			if (act[q]) d[q] = p[(long long)(SWEEP_THREADS / 4) * q * 4];
+		}
+#pragma unroll
+		for (int q = 0; q < SWEEP_U; q++) {
+			if (!act[q]) continue;
+			const unsigned lo = (unsigned)cf[q], hi = (unsigned)(cf[q] >> 32);
+			uint4 v = d[q];
+			xor4(v, Tc[(0 * 256 + (lo & 255)) * 4]);
+			xor4(v, Tc[(1 * 256 + ((lo >> 8) & 255)) * 4]);
+			xor4(v, Tc[(2 * 256 + ((lo >> 16) & 255)) * 4]);
+			xor4(v, Tc[(3 * 256 + (lo >> 24)) * 4]);
+			xor4(v, Tc[(4 * 256 + (hi & 255)) * 4]);
+			xor4(v, Tc[(5 * 256 + ((hi >> 8) & 255)) * 4]);
+			xor4(v, Tc[(6 * 256 + ((hi >> 16) & 255)) * 4]);
+			xor4(v, Tc[(7 * 256 + (hi >> 24)) * 4]);
+			p[(long long)(SWEEP_THREADS / 4) * q * 4] = v;
+			if (force && ch == nch) {
+				long long row = row0 + (SWEEP_THREADS / 4) * q;
+				pc_next[row] = (wn & 1) ? (((u64)v.w << 32) | v.z) : (((u64)v.y << 32) | v.x);
+			}
+		}
+	}
+}
+
+/* any active row (i >= rank) with b = 1 makes the system inconsistent
+ * (_mzd_pluq_solve_left's check, _internal.c:440-446 -> None) */
+__global__ void k_check(Mat M, SolverState *st) {
+	const long long r = st->r;
+	int bad = 0;
+	for (long long i = r + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M.m;
+	     i += (long long)gridDim.x * blockDim.x)
+		bad |= (int)(M.base[widx(M, i, M.nw)] & 1);
+	if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&st->inconsistent, 1);
+}
+
+/* ------------------------------------------------------------------------
+ * k_backsub: back-substitution over the echelon rows, last panel first.
+ * One CTA per right-hand side; x (extended with x[nw] = use_b so the b word is
+ * just another column) lives in shared memory.  rhs 0 with use_b = 1 is the
+ * particular solution (free variables 0, _internal.c:440-454); with freecols !=
+ * nullptr CTA i computes the kernel vector that is 1 at free column freecols[i]
+ * and 0 at the other free columns (_internal.c:330-348: U1^-1 U2 ; I).
+ * ---------------------------------------------------------------------- */
+__global__ void __launch_bounds__(1024, 1)
+k_backsub(Mat M, const long long *__restrict__ hist_r, const u64 *__restrict__ hist_pm,
+          const long long *__restrict__ freecols, int use_b, u64 *__restrict__ xout) {
+	extern __shared__ u64 xs[];
+	__shared__ unsigned long long newbits;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int WT = M.ns * 8;
+	for (int w = tid; w < WT; w += blockDim.x) xs[w] = 0;
+	__syncthreads();
+	if (tid == 0) {
+		if (use_b) xs[M.nw] = 1;
+		if (freecols) {
+			long long f = freecols[blockIdx.x];
+			xs[f >> 6] |= 1ULL << (f & 63);
+		}
+		newbits = 0;
+	}
+	__syncthreads();
+	const int wl = lane & 7, so = lane >> 3;
+	for (int p = M.nw - 1; p >= 0; --p) {
+		const u64 pm = hist_pm[p];
+		if (!pm) continue;
+		const int k = __popcll(pm);
+		const long long r = hist_r[p];
+		for (int j = warp; j < k; j += 32) {
+			const u64 *rowp = M.base + (r + j) * 8 + wl;
+			u64 acc = 0;
+			int s = (p >> 3) + so;
+#pragma unroll 4
+			for (; s < M.ns; s += 4) {
+				int wd = s * 8 + wl;
+				u64 a = rowp[(long long)s * M.mp * 8];
+				if (wd >= p) acc ^= a & xs[wd];
+			}
+			int par = __popcll(acc) & 1;
+			par = __reduce_xor_sync(0xffffffffu, par);
+			if (lane == 0 && par) {
+				u64 t = pm;
+				for (int q = 0; q < j; q++) t &= t - 1;
+				atomicOr(&newbits, t & (~t + 1));
+			}
+		}
+		__syncthreads();
+		if (tid == 0) {
+			xs[p] |= newbits;
+			newbits = 0;
+		}
+		__syncthreads();
+	}
+	for (int w = tid; w < M.nw; w += blockDim.x) xout[(long long)blockIdx.x * M.nw + w] = xs[w];
+}
+
+} /* namespace gf2b200 */
