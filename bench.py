@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- GF(2) n x n echelonize throughput (bit-ops/s) on B200 vs the CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n SIZE]
+
+A "step" is one full solve (forward elimination with 64-column panels, consistency
+check, back-substitution of the particular solution) of the dense synthetic system
+of SURVEY.md 8(d).  W(n) = n^3/3 bit-ops per step (dense schoolbook count, the same
+W for CPU and GPU).  N = 1: n = 131072 (BASELINE.json configs[3], the config the
+metric's target is quoted on); N > 1: n = 524288 row-sharded (configs[4]).
+
+`value`  : device-resident: the system is generated in HBM (untimed), the timed
+           region is gf2b200_system_eliminate, CUDA events on the solver stream,
+           max over ranks.
+`e2e`    : the same solve through gf2b200_solve() -- the call the reference-side
+           extension makes in place of M4RI -- with HOST (pinned) A and b: H2D, layout,
+           eliminate, back-substitute and D2H of the solution inside the timed region.
+`roofline`: k_sweep (the row-XOR sweep, the dominant kernel): algorithmic bytes
+           (2 * rows * 64 B * strips per launch) / CUDA-event duration of every
+           sweep launch of one profiled step, against MEASURED_PEAKS.json hbm_gbs.
+`cpu_baseline`: the oracle's blocked Four-Russians port (oracle/gf2_oracle.c,
+           "port": M4RI itself is absent from the image) on the host cores, on a
+           bounded sample (same generator, smaller n).
+--impl reference: the CPU port alone, on host cores, same metric/config keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "GF(2) n x n echelonize bit-ops/s (W = n^3/3 per solve)"
+UNIT = "bit-ops/s"
+PHI = 0x9E3779B97F4A7C15
+
+
+def work(n: int) -> float:
+    return float(n) ** 3 / 3.0
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8 or not (t0 - 0.1 <= ts <= t1 + 0.3):
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- host inputs for e2e
+def host_system_pinned(n: int, seed: int):
+    """The synthetic system in PINNED host memory (numpy views of torch pinned tensors)."""
+    import numpy as np
+    import torch
+
+    nw = (n + 63) // 64
+    tA = torch.empty((n, nw), dtype=torch.int64, pin_memory=True)
+    tb = torch.zeros(((n + 63) // 64,), dtype=torch.int64, pin_memory=True)
+    A = tA.numpy().view(np.uint64)
+    b = tb.numpy().view(np.uint64)
+
+    def mix(z):
+        z ^= z >> np.uint64(30); z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27); z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+        return z
+
+    with np.errstate(over="ignore"):
+        phi = np.uint64(PHI)
+        x = mix(np.uint64(seed ^ 0xB200) + phi * np.arange(1, nw + 1, dtype=np.uint64))
+        tail = np.uint64((1 << (n & 63)) - 1) if n & 63 else None
+        if tail is not None:
+            x[-1] &= tail
+        rows_per = max(1, (32 << 20) // (nw * 8))
+        bbits = np.zeros(((n + 63) // 64) * 64, dtype=np.uint8)
+        wi = np.arange(1, nw + 1, dtype=np.uint64)
+        for r0 in range(0, n, rows_per):
+            r1 = min(n, r0 + rows_per)
+            idx = (np.arange(r0, r1, dtype=np.uint64)[:, None] * np.uint64(nw)) + wi[None, :]
+            blk = mix(np.uint64(seed) + phi * idx)
+            if tail is not None:
+                blk[:, -1] &= tail
+            A[r0:r1] = blk
+            acc = np.bitwise_xor.reduce(blk & x[None, :], axis=1)
+            par = np.unpackbits(acc.view(np.uint8).reshape(-1, 8), axis=1).sum(axis=1) & 1
+            bbits[r0:r1] = par
+        b[:] = np.packbits(bbits, bitorder="little").view(np.uint64)
+    return tA, tb, A, b
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_port_run(n: int, seed: int = 1):
+    """One solve of the n x n synthetic system by the oracle's Four-Russians port."""
+    import oracle  # the checker, timed here only as the CPU baseline / reference arm
+
+    A, b, _ = oracle.synth(n, n, seed)
+    t0 = time.perf_counter()
+    sol = oracle.solve_packed(A, b, n, 0, tier="m4rm")
+    dt = time.perf_counter() - t0
+    assert sol.status == 0
+    return dt, oracle.threads()
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    n_cfg = args.n or (131072 if args.gpus == 1 else 524288)
+    steps, warm = args.steps, args.warmup
+    # bounded sample: n_s sized so the whole run stays within a few minutes
+    n_s = 16384 if (steps + warm) > 6 else 32768
+    if args.sample_n:
+        n_s = args.sample_n
+    for _ in range(warm):
+        cpu_port_run(n_s)
+    ts, cores = [], 1
+    for _ in range(steps):
+        dt, cores = cpu_port_run(n_s)
+        ts.append(dt)
+    tot = sum(ts)
+    val = steps * work(n_s) / tot
+    sample = f"dense synthetic n={n_s} (same generator, seed 1), full solve, extrapolates as n^3"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * tot / steps, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"dense random {n_cfg}x{n_cfg} GF(2) echelonize + solve",
+                   "n": n_cfg, "timed_sample_n": n_s,
+                   "note": "CPU port of the reference's M4RI path (M4RI itself is not in the image); "
+                           "bit-ops/s measured on the bounded sample"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_b200(args, rank: int, world: int, local_rank: int):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from gf2bv_b200 import _shim
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- gf2bv_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    n = args.n or (131072 if world == 1 else 524288)
+    seed = 1
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(_shim.Context.nccl_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        ctx = _shim.Context(local_rank, rank, world, bytes(idt.cpu().numpy().tobytes()))
+    else:
+        ctx = _shim.Context(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sysm = ctx.system(n, n)
+    steps, warm = args.steps, args.warmup
+
+    def one_step():
+        sysm.generate(seed)       # inputs resident in HBM before the timed region
+        barrier()
+        sysm.eliminate()          # timed on the device (CUDA events inside, stream-ordered)
+        st = sysm.stats()
+        return st
+
+    for _ in range(warm):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_wall0 = time.time()
+    ms, launches, st = [], 0, None
+    for _ in range(steps):
+        st = one_step()
+        ms.append(st["ms_total"])
+        launches += st["kernel_launches"]
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    tot_ms = float(sum(ms))
+    if world > 1:
+        t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_ms = float(t.item())
+    res = sysm.result(0)
+    bad = sysm.check_synthetic(seed, res.origin) if res.status == 0 else -1
+    if world > 1:
+        t = torch.tensor([bad], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        bad = int(t.item())
+    if res.status != 0 or bad != 0:
+        raise SystemExit(f"bench.py: solution check failed (status {res.status}, bad rows {bad})")
+    value = steps * work(n) / (tot_ms / 1e3)
+
+    # ---- roofline of the sweep kernel: one extra profiled step (events around every k_sweep)
+    ctx.set_profile(True)
+    stp = one_step()
+    ctx.set_profile(False)
+    peak, peak_src = hbm_peak()
+    achieved = stp["sweep_bytes"] / (stp["ms_sweep"] / 1e3) / 1e9 if stp["ms_sweep"] else 0.0
+    traffic = None
+    tp = ROOT / "profiles" / "sweep_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "k_sweep", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": stp["sweep_bytes"] / max(1, stp["sweep_launches"]),
+        "avg_launch_ms": stp["ms_sweep"] / max(1, stp["sweep_launches"]),
+        "launches_per_step": stp["sweep_launches"],
+        "sweep_share_of_step": stp["ms_sweep"] / stp["ms_total"],
+        "largest_launch": {"bytes": stp["sweep_bytes_max"], "ms": stp["ms_sweep_max"],
+                           "GBs": stp["sweep_bytes_max"] / stp["ms_sweep_max"] / 1e6 if stp["ms_sweep_max"] else None},
+    }
+
+    # ---- e2e through the C-ABI host-buffer call (N = 1; sharded runs load per-rank rows)
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        tA, tb, A, b = host_system_pinned(n, seed)
+        e_steps = steps if steps <= 3 else 3
+        ctx.solve(A, b, n, 0)  # warm-up (allocations, pinned mappings)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            r = ctx.solve(A, b, n, 0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert r.status == 0 and np.array_equal(r.origin, res.origin)
+        e2e = {"value": e_steps * work(n) / dt, "unit": UNIT, "steps": e_steps, "ms_per_step": 1e3 * dt / e_steps,
+               "h2d_bytes_per_step": int(A.nbytes + b.nbytes),
+               "d2h_bytes_per_step": int(res.origin.nbytes + 2 * 8 * ((n + 63) // 64) + 16),
+               "api": "gf2b200_solve(ctx, A_host_pinned, b_host, m, n, stride64, mode=0, &result)"}
+        del tA, tb
+
+    # ---- CPU baseline (rank 0, N = 1): the oracle's port on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n_s = args.sample_n or 32768
+        dt, cores = cpu_port_run(n_s)
+        cpu = {"value": work(n_s) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"dense synthetic n={n_s} (same generator, seed 1), one full solve in {dt:.1f} s; "
+                         "oracle/gf2_oracle.c Four-Russians port with OpenMP (M4RI is not in the image)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": tot_ms / steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"dense random {n}x{n} GF(2) echelonize + solve (BASELINE.json configs[{3 if n == 131072 else 4 if n == 524288 else '-'}])",
+                       "n": n, "seed": seed, "rank": int(res.rank), "panel_bits": 64,
+                       "l2": "inputs larger than L2 (matrix %.1f GB, regenerated every step)" % (n * n / 8 / 1e9),
+                       "sharding": "single GPU" if world == 1 else f"row blocks over {world} GPUs, NCCL pivot-row exchange"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "residual_bad_rows": bad,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--sample-n", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py: --gpus N > 1 must be launched under torch.distributed.run (one rank per GPU)")
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
