@@ -25,6 +25,7 @@ EXPORTS = [
     "gf2b200_system_destroy", "gf2b200_system_local_rows", "gf2b200_system_load_host",
     "gf2b200_system_load_device", "gf2b200_system_generate", "gf2b200_system_eliminate",
     "gf2b200_system_result", "gf2b200_system_stats", "gf2b200_system_check_synthetic",
+    "gf2b200_host_alloc", "gf2b200_host_free",
 ]
 
 

@@ -153,6 +153,24 @@ extern "C" int gf2b200_set_profile(gf2b200_ctx *ctx, int profile) {
 	return GF2B200_OK;
 }
 
+extern "C" int gf2b200_host_alloc(void **out, size_t bytes) {
+	if (!out) return fail(nullptr, GF2B200_EINVAL, "out is NULL");
+	*out = nullptr;
+	if (gf2b200_device_count() <= 0)
+		return fail(nullptr, GF2B200_ENODEV, "no CUDA device: libgf2b200 has no CPU fallback");
+	cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		*out = nullptr;
+		return fail(nullptr, GF2B200_ENOMEM, "cudaHostAlloc: %s", cudaGetErrorString(e));
+	}
+	return GF2B200_OK;
+}
+
+extern "C" void gf2b200_host_free(void *p) {
+	if (p) cudaFreeHost(p);
+}
+
 extern "C" void gf2b200_result_free(gf2b200_result *res) {
 	if (!res) return;
 	free(res->origin);

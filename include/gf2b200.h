@@ -85,6 +85,12 @@ int gf2b200_create_dist(gf2b200_ctx **out, int device, int rank, int world,
 void gf2b200_destroy(gf2b200_ctx *ctx);
 const char *gf2b200_last_error(const gf2b200_ctx *ctx);
 
+/* Page-locked host memory for the caller's packed A / b (full-speed, truly
+ * asynchronous H2D).  The extension packs PyLongs straight into such a buffer
+ * (replaces mzd_init for A and B, _internal.c:398-399). */
+int gf2b200_host_alloc(void **out, size_t bytes);
+void gf2b200_host_free(void *p);
+
 /* Run on the caller's CUDA stream (a cudaStream_t passed as void*); NULL = the
  * context's own stream.  profile != 0 brackets every sweep launch with events. */
 int gf2b200_set_stream(gf2b200_ctx *ctx, void *cuda_stream);
