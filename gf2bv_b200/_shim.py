@@ -25,7 +25,7 @@ EXPORTS = [
     "gf2b200_system_destroy", "gf2b200_system_local_rows", "gf2b200_system_load_host",
     "gf2b200_system_load_device", "gf2b200_system_generate", "gf2b200_system_eliminate",
     "gf2b200_system_result", "gf2b200_system_stats", "gf2b200_system_check_synthetic",
-    "gf2b200_host_alloc", "gf2b200_host_free",
+    "gf2b200_host_alloc", "gf2b200_host_free", "gf2b200_create_shards",
 ]
 
 
@@ -59,6 +59,8 @@ class CStats(ctypes.Structure):
         ("m_local", ctypes.c_int64),
         ("ms_sweep_max", ctypes.c_double),
         ("sweep_bytes_max", ctypes.c_double),
+        ("sweep_bytes_timed", ctypes.c_double),
+        ("sweep_launches_timed", ctypes.c_int64),
     ]
 
     def as_dict(self):
@@ -84,6 +86,10 @@ def lib() -> ctypes.CDLL:
     L.gf2b200_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
     L.gf2b200_nccl_unique_id.argtypes = [vp]
     L.gf2b200_create_dist.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+    L.gf2b200_create_shards.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int]
+    L.gf2b200_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+    L.gf2b200_host_free.argtypes = [vp]
+    L.gf2b200_host_free.restype = None
     L.gf2b200_destroy.argtypes = [vp]
     L.gf2b200_destroy.restype = None
     L.gf2b200_last_error.argtypes = [vp]
@@ -137,10 +143,15 @@ class Context:
     """One solver context (device + stream).  ``rank/world/nccl_id`` select the
     row-sharded multi-GPU mode (one process per GPU)."""
 
-    def __init__(self, device: int = 0, rank: int = 0, world: int = 1, nccl_id: Optional[bytes] = None):
+    def __init__(self, device: int = 0, rank: int = 0, world: int = 1, nccl_id: Optional[bytes] = None,
+                 shards: int = 0):
         L = lib()
         self._h = ctypes.c_void_p()
-        if world > 1:
+        if shards:
+            # loopback: `shards` row shards on this one device (tests the sharded path on 1 GPU)
+            rc = L.gf2b200_create_shards(ctypes.byref(self._h), device, shards)
+            world = shards
+        elif world > 1:
             buf = ctypes.create_string_buffer(nccl_id, 128)
             rc = L.gf2b200_create_dist(ctypes.byref(self._h), device, rank, world, buf)
         else:

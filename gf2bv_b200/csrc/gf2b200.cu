@@ -1,12 +1,23 @@
 /*
  * gf2b200.cu -- host side of libgf2b200.so: the C-ABI declared in
- * include/gf2b200.h on top of the sm_100a kernels in gf2b200_kernels.cuh.
+ * include/gf2b200.h on top of the sm_100a kernels in gf2b200_kernels.cuh (panel
+ * select / apply / sweep) and gf2b200_dist.cuh (row-sharded election, pivot-row
+ * exchange, blocked back-substitution).
  *
  * Stands where M4RI stands behind gf2bv/_internal.c:429-489 (PLUQ + solve +
  * kernel basis).  No CPU fallback: every entry point needs a CUDA device.
+ *
+ * A system is a set of row shards.  Three kinds of context:
+ *   single    one shard on one GPU (gf2b200_create);
+ *   nccl      one shard per process/GPU, exchanges over NCCL (gf2b200_create_dist);
+ *   loopback  `world` shards on ONE GPU in one process, exchanges are device
+ *             copies (gf2b200_create_shards) -- same kernels and control flow as
+ *             the nccl kind, so the sharded path can be parity-tested on one GPU.
  */
-#include "gf2b200_kernels.cuh"
+#include "gf2b200_dist.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -18,31 +29,59 @@
 
 using namespace gf2b200;
 
+/* ---- NCCL, resolved at run time (torch's bundled libnccl.so.2 when the caller
+ * already loaded it, else the system one) ---------------------------------- */
+struct NcclApi {
+	void *handle;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+	ncclResult_t (*CommDestroy)(ncclComm_t);
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+	const char *(*GetErrorString)(ncclResult_t);
+};
+static NcclApi g_nccl;
+
 struct gf2b200_ctx {
 	int device;
 	int n_sm;
 	cudaStream_t own_stream;
 	cudaStream_t stream;
 	int profile;
-	int rank, world;
-	void *nccl; /* ncclComm_t (dist contexts) */
+	int rank, world; /* shard index of the first local shard, number of shards */
+	int n_local;     /* local shards: 1 (single, nccl) or world (loopback) */
+	ncclComm_t nccl; /* nccl contexts */
 	char err[512];
 };
 
-struct gf2b200_system {
-	gf2b200_ctx *ctx;
-	long long m_global, n;
-	long long row_begin; /* first global row held here */
+struct Shard {
 	Mat M;
+	int index;           /* global shard index */
+	long long row_begin; /* first global row */
 	u64 *d_pc[2];
 	SolverState *d_state;
 	PanelDesc *d_pd;
 	long long *d_hist_r;
 	u64 *d_hist_pm;
 	uint4 *d_ebuf;
-	u64 *d_x; /* particular solution, nw words */
+	/* sharded systems only */
+	DistPanel *d_dp;
+	unsigned char *d_hist_owner;
+	u64 *d_cand_send, *d_cand_all;
+	int *d_selrow;
+	uint4 *d_rows_send, *d_rows_all;
+	/* back-substitution */
+	u64 *d_x;    /* nw + 1 words */
+	u64 *d_slab; /* BS_S*64 rows x BS_W */
+	u64 *d_slab_all;
 	std::vector<long long> hist_r;
+};
+
+struct gf2b200_system {
+	gf2b200_ctx *ctx;
+	long long m_global, n;
+	std::vector<Shard> sh;
 	std::vector<u64> hist_pm;
+	std::vector<unsigned char> hist_owner;
 	long long rank;
 	int inconsistent;
 	int eliminated;
@@ -68,6 +107,13 @@ static int fail(gf2b200_ctx *ctx, int code, const char *fmt, const char *a = "",
 			            "%s: %s", #call, cudaGetErrorString(e_));                          \
 	} while (0)
 
+#define NK(ctx, call)                                                                    \
+	do {                                                                                 \
+		ncclResult_t r_ = (call);                                                        \
+		if (r_ != ncclSuccess)                                                           \
+			return fail(ctx, GF2B200_ENCCL, "%s: %s", #call, g_nccl.GetErrorString(r_)); \
+	} while (0)
+
 extern "C" int gf2b200_abi_version(void) { return GF2B200_ABI_VERSION; }
 
 extern "C" int gf2b200_device_count(void) {
@@ -81,6 +127,24 @@ extern "C" int gf2b200_device_count(void) {
 
 extern "C" const char *gf2b200_last_error(const gf2b200_ctx *ctx) { return ctx ? ctx->err : g_err; }
 
+static int nccl_load(void) {
+	if (g_nccl.handle) return 0;
+	void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+	if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) return fail(nullptr, GF2B200_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+	NcclApi a;
+	a.handle = h;
+	*(void **)&a.GetUniqueId = dlsym(h, "ncclGetUniqueId");
+	*(void **)&a.CommInitRank = dlsym(h, "ncclCommInitRank");
+	*(void **)&a.CommDestroy = dlsym(h, "ncclCommDestroy");
+	*(void **)&a.AllGather = dlsym(h, "ncclAllGather");
+	*(void **)&a.GetErrorString = dlsym(h, "ncclGetErrorString");
+	if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.GetErrorString)
+		return fail(nullptr, GF2B200_ENCCL, "libnccl.so.2 lacks a required symbol");
+	g_nccl = a;
+	return 0;
+}
+
 static int ctx_init(gf2b200_ctx **out, int device) {
 	if (!out) return fail(nullptr, GF2B200_EINVAL, "out is NULL");
 	*out = nullptr;
@@ -92,6 +156,7 @@ static int ctx_init(gf2b200_ctx **out, int device) {
 	if (!c) return fail(nullptr, GF2B200_ENOMEM, "calloc");
 	c->device = device;
 	c->world = 1;
+	c->n_local = 1;
 	cudaError_t e = cudaSetDevice(device);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
 	cudaDeviceProp prop;
@@ -121,22 +186,54 @@ static int ctx_init(gf2b200_ctx **out, int device) {
 
 extern "C" int gf2b200_create(gf2b200_ctx **out, int device) { return ctx_init(out, device); }
 
+extern "C" int gf2b200_create_shards(gf2b200_ctx **out, int device, int world) {
+	if (out) *out = nullptr;
+	if (world < 1 || world > 64) return fail(nullptr, GF2B200_EINVAL, "world must be in 1..64");
+	int rc = ctx_init(out, device);
+	if (rc) return rc;
+	(*out)->world = world;
+	(*out)->n_local = world;
+	return GF2B200_OK;
+}
+
 extern "C" int gf2b200_nccl_unique_id(void *out_id128) {
-	(void)out_id128;
-	return fail(nullptr, GF2B200_ENCCL, "multi-GPU path not built yet");
+	if (!out_id128) return fail(nullptr, GF2B200_EINVAL, "out is NULL");
+	if (nccl_load()) return GF2B200_ENCCL;
+	ncclUniqueId id;
+	NK(nullptr, g_nccl.GetUniqueId(&id));
+	memcpy(out_id128, &id, sizeof id);
+	return GF2B200_OK;
 }
 
 extern "C" int gf2b200_create_dist(gf2b200_ctx **out, int device, int rank, int world,
                                    const void *nccl_id128) {
-	(void)device; (void)rank; (void)nccl_id128;
 	if (out) *out = nullptr;
 	if (world == 1) return ctx_init(out, device);
-	return fail(nullptr, GF2B200_ENCCL, "multi-GPU path not built yet");
+	if (world < 1 || world > 64 || rank < 0 || rank >= world || !nccl_id128)
+		return fail(nullptr, GF2B200_EINVAL, "bad rank/world/id");
+	if (nccl_load()) return GF2B200_ENCCL;
+	int rc = ctx_init(out, device);
+	if (rc) return rc;
+	gf2b200_ctx *c = *out;
+	c->rank = rank;
+	c->world = world;
+	ncclUniqueId id;
+	memcpy(&id, nccl_id128, sizeof id);
+	ncclResult_t r = g_nccl.CommInitRank(&c->nccl, world, id, rank);
+	if (r != ncclSuccess) {
+		rc = fail(nullptr, GF2B200_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+		c->nccl = nullptr;
+		gf2b200_destroy(c);
+		*out = nullptr;
+		return rc;
+	}
+	return GF2B200_OK;
 }
 
 extern "C" void gf2b200_destroy(gf2b200_ctx *ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
+	if (ctx->nccl) g_nccl.CommDestroy(ctx->nccl);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
 	free(ctx);
 }
@@ -182,20 +279,60 @@ extern "C" void gf2b200_result_free(gf2b200_result *res) {
 
 /* ---- systems -------------------------------------------------------------- */
 
+static void shard_free(Shard &s) {
+	cudaFree(s.M.base);
+	cudaFree(s.d_pc[0]);
+	cudaFree(s.d_pc[1]);
+	cudaFree(s.d_state);
+	cudaFree(s.d_pd);
+	cudaFree(s.d_hist_r);
+	cudaFree(s.d_hist_pm);
+	cudaFree(s.d_ebuf);
+	cudaFree(s.d_dp);
+	cudaFree(s.d_hist_owner);
+	cudaFree(s.d_cand_send);
+	cudaFree(s.d_cand_all);
+	cudaFree(s.d_selrow);
+	cudaFree(s.d_rows_send);
+	cudaFree(s.d_rows_all);
+	cudaFree(s.d_x);
+	if (s.d_slab_all != s.d_slab) cudaFree(s.d_slab_all);
+	cudaFree(s.d_slab);
+}
+
 extern "C" void gf2b200_system_destroy(gf2b200_system *sys) {
 	if (!sys) return;
 	cudaSetDevice(sys->ctx->device);
-	cudaFree(sys->M.base);
-	cudaFree(sys->d_pc[0]);
-	cudaFree(sys->d_pc[1]);
-	cudaFree(sys->d_state);
-	cudaFree(sys->d_pd);
-	cudaFree(sys->d_hist_r);
-	cudaFree(sys->d_hist_pm);
-	cudaFree(sys->d_ebuf);
-	cudaFree(sys->d_x);
+	for (Shard &s : sys->sh) shard_free(s);
 	for (cudaEvent_t e : sys->ev) cudaEventDestroy(e);
 	delete sys;
+}
+
+static cudaError_t shard_alloc(Shard &s, int world) {
+	const Mat &M = s.M;
+	cudaError_t e = cudaMalloc(&s.M.base, (size_t)M.ns * (size_t)M.mp * 64);
+	if (e == cudaSuccess) e = cudaMalloc(&s.d_pc[0], (size_t)M.mp * 8);
+	if (e == cudaSuccess) e = cudaMalloc(&s.d_pc[1], (size_t)M.mp * 8);
+	if (e == cudaSuccess) e = cudaMalloc(&s.d_state, sizeof(SolverState));
+	if (e == cudaSuccess) e = cudaMalloc(&s.d_pd, sizeof(PanelDesc));
+	if (e == cudaSuccess) e = cudaMalloc(&s.d_hist_r, (size_t)M.nw * 8);
+	if (e == cudaSuccess) e = cudaMalloc(&s.d_hist_pm, (size_t)M.nw * 8);
+	if (e == cudaSuccess) e = cudaMalloc(&s.d_ebuf, (size_t)M.ns * 4096);
+	if (e == cudaSuccess) e = cudaMalloc(&s.d_x, (size_t)(M.nw + 1) * 8);
+	if (e == cudaSuccess) e = cudaMalloc(&s.d_slab, (size_t)BS_S * 64 * BS_W * 8);
+	s.d_slab_all = s.d_slab;
+	if (world > 1) {
+		s.d_slab_all = nullptr;
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_slab_all, (size_t)world * BS_S * 64 * BS_W * 8);
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_dp, sizeof(DistPanel));
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_hist_owner, (size_t)M.nw * 64);
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_cand_send, CAND_W * 8);
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_cand_all, (size_t)world * CAND_W * 8);
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_selrow, 64 * sizeof(int));
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_rows_send, (size_t)64 * M.ns * 64);
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_rows_all, (size_t)world * 64 * M.ns * 64);
+	}
+	return e;
 }
 
 extern "C" int gf2b200_system_create(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2b200_system **out) {
@@ -209,30 +346,32 @@ extern "C" int gf2b200_system_create(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2
 	s->ctx = ctx;
 	s->m_global = m;
 	s->n = n;
-	long long r0 = m * ctx->rank / ctx->world, r1 = m * (ctx->rank + 1) / ctx->world;
-	s->row_begin = r0;
-	Mat &M = s->M;
-	M.m = r1 - r0;
-	M.n = n;
-	M.nw = (int)((n + 63) / 64);
-	M.ns = (M.nw + 1 + 7) / 8;
-	M.mp = (std::max<long long>(M.m, 1) + 15) / 16 * 16;
-	M.base = nullptr;
-	s->d_pc[0] = s->d_pc[1] = nullptr;
-	s->d_state = nullptr; s->d_pd = nullptr; s->d_hist_r = nullptr; s->d_hist_pm = nullptr;
-	s->d_ebuf = nullptr; s->d_x = nullptr;
-	s->rank = 0; s->inconsistent = 0; s->eliminated = 0;
+	s->rank = 0;
+	s->inconsistent = 0;
+	s->eliminated = 0;
 	memset(&s->stats, 0, sizeof s->stats);
-	size_t mat_bytes = (size_t)M.ns * (size_t)M.mp * 64;
-	cudaError_t e = cudaMalloc(&M.base, mat_bytes);
-	if (e == cudaSuccess) e = cudaMalloc(&s->d_pc[0], (size_t)M.mp * 8);
-	if (e == cudaSuccess) e = cudaMalloc(&s->d_pc[1], (size_t)M.mp * 8);
-	if (e == cudaSuccess) e = cudaMalloc(&s->d_state, sizeof(SolverState));
-	if (e == cudaSuccess) e = cudaMalloc(&s->d_pd, sizeof(PanelDesc));
-	if (e == cudaSuccess) e = cudaMalloc(&s->d_hist_r, (size_t)M.nw * 8);
-	if (e == cudaSuccess) e = cudaMalloc(&s->d_hist_pm, (size_t)M.nw * 8);
-	if (e == cudaSuccess) e = cudaMalloc(&s->d_ebuf, (size_t)M.ns * 4096);
-	if (e == cudaSuccess) e = cudaMalloc(&s->d_x, (size_t)M.nw * 8);
+	s->sh.resize(ctx->n_local);
+	cudaError_t e = cudaSuccess;
+	for (int l = 0; l < ctx->n_local && e == cudaSuccess; l++) {
+		Shard &h = s->sh[l];
+		h.index = ctx->rank + l;
+		long long r0 = m * h.index / ctx->world, r1 = m * (h.index + 1) / ctx->world;
+		h.row_begin = r0;
+		Mat &M = h.M;
+		M.base = nullptr;
+		M.m = r1 - r0;
+		M.n = n;
+		M.nw = (int)((n + 63) / 64);
+		M.ns = (M.nw + 1 + 7) / 8;
+		M.mp = (std::max<long long>(M.m, 1) + 15) / 16 * 16;
+		h.d_pc[0] = h.d_pc[1] = nullptr;
+		h.d_state = nullptr; h.d_pd = nullptr; h.d_hist_r = nullptr; h.d_hist_pm = nullptr;
+		h.d_ebuf = nullptr; h.d_dp = nullptr; h.d_hist_owner = nullptr;
+		h.d_cand_send = h.d_cand_all = nullptr; h.d_selrow = nullptr;
+		h.d_rows_send = h.d_rows_all = nullptr;
+		h.d_x = h.d_slab = h.d_slab_all = nullptr;
+		e = shard_alloc(h, ctx->world);
+	}
 	if (e != cudaSuccess) {
 		int rc = fail(ctx, e == cudaErrorMemoryAllocation ? GF2B200_ENOMEM : GF2B200_ECUDA,
 		              "system_create: %s", cudaGetErrorString(e));
@@ -244,7 +383,12 @@ extern "C" int gf2b200_system_create(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2
 	return GF2B200_OK;
 }
 
-extern "C" int64_t gf2b200_system_local_rows(const gf2b200_system *sys) { return sys ? sys->M.m : -1; }
+extern "C" int64_t gf2b200_system_local_rows(const gf2b200_system *sys) {
+	if (!sys) return -1;
+	long long t = 0;
+	for (const Shard &s : sys->sh) t += s.M.m;
+	return t;
+}
 
 static int grid_for(long long items, int threads, int cap) {
 	long long g = (items + threads - 1) / threads;
@@ -257,11 +401,16 @@ extern "C" int gf2b200_system_load_device(gf2b200_system *sys, const uint64_t *d
                                           const uint64_t *db, int64_t stride64) {
 	if (!sys || !dA) return fail(sys ? sys->ctx : nullptr, GF2B200_EINVAL, "NULL argument");
 	gf2b200_ctx *ctx = sys->ctx;
-	if (stride64 < sys->M.nw) return fail(ctx, GF2B200_EINVAL, "stride64 < ceil(n/64)");
+	if (stride64 < sys->sh[0].M.nw) return fail(ctx, GF2B200_EINVAL, "stride64 < ceil(n/64)");
 	CK(ctx, cudaSetDevice(ctx->device));
-	long long total = sys->M.m * sys->M.ns * 8;
-	k_layout<<<grid_for(total, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
-	    sys->M, (const u64 *)dA, (const u64 *)db, stride64, 0, sys->M.m, 0);
+	const long long base = sys->sh[0].row_begin; /* dA / db start at the first local row */
+	for (Shard &h : sys->sh) {
+		if (h.M.m == 0) continue;
+		long long total = h.M.m * h.M.ns * 8;
+		long long off = h.row_begin - base;
+		k_layout<<<grid_for(total, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
+		    h.M, (const u64 *)dA + off * stride64, (const u64 *)db, stride64, 0, h.M.m, off);
+	}
 	CK(ctx, cudaGetLastError());
 	sys->eliminated = 0;
 	return GF2B200_OK;
@@ -271,43 +420,66 @@ extern "C" int gf2b200_system_load_host(gf2b200_system *sys, const uint64_t *A, 
                                         int64_t stride64) {
 	if (!sys || !A) return fail(sys ? sys->ctx : nullptr, GF2B200_EINVAL, "NULL argument");
 	gf2b200_ctx *ctx = sys->ctx;
-	const Mat &M = sys->M;
-	if (stride64 < M.nw) return fail(ctx, GF2B200_EINVAL, "stride64 < ceil(n/64)");
+	if (stride64 < sys->sh[0].M.nw) return fail(ctx, GF2B200_EINVAL, "stride64 < ceil(n/64)");
 	CK(ctx, cudaSetDevice(ctx->device));
-	/* rows travel in chunks through two device staging buffers so the layout
-	 * kernel of chunk c overlaps the H2D copy of chunk c+1 */
+	const long long m_loc = gf2b200_system_local_rows(sys);
+	const long long base = sys->sh[0].row_begin;
+	/* rows travel in chunks through two device staging buffers: the copy of chunk
+	 * c+1 (copy stream) overlaps the layout kernel of chunk c (solver stream) */
 	const size_t row_bytes = (size_t)stride64 * 8;
 	long long chunk_rows = std::max<long long>(1, (long long)((64u << 20) / row_bytes));
-	chunk_rows = std::min<long long>(chunk_rows, M.m);
+	chunk_rows = std::min<long long>(chunk_rows, std::max<long long>(m_loc, 1));
 	u64 *stage[2] = {nullptr, nullptr};
 	u64 *d_b = nullptr;
-	cudaEvent_t done[2] = {nullptr, nullptr};
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t copied[2] = {nullptr, nullptr}, laid[2] = {nullptr, nullptr};
 	int rc = GF2B200_OK;
 	cudaError_t e = cudaMalloc(&stage[0], chunk_rows * row_bytes);
-	if (e == cudaSuccess && chunk_rows < M.m) e = cudaMalloc(&stage[1], chunk_rows * row_bytes);
-	if (e == cudaSuccess && b) e = cudaMalloc(&d_b, (size_t)((M.m + 63) / 64) * 8);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming);
+	if (e == cudaSuccess && chunk_rows < m_loc) e = cudaMalloc(&stage[1], chunk_rows * row_bytes);
+	if (e == cudaSuccess && b) e = cudaMalloc(&d_b, (size_t)((m_loc + 63) / 64) * 8);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
+	for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+		e = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&laid[i], cudaEventDisableTiming);
+	}
 	if (e == cudaSuccess && b)
-		e = cudaMemcpyAsync(d_b, b, (size_t)((M.m + 63) / 64) * 8, cudaMemcpyHostToDevice, ctx->stream);
-	int ci = 0;
-	for (long long row0 = 0; e == cudaSuccess && row0 < M.m; row0 += chunk_rows, ci ^= 1) {
-		long long nr = std::min<long long>(chunk_rows, M.m - row0);
-		u64 *st = stage[1] ? stage[ci] : stage[0];
-		e = cudaMemcpyAsync(st, A + row0 * stride64, nr * row_bytes, cudaMemcpyHostToDevice, ctx->stream);
-		if (e != cudaSuccess) break;
-		long long total = nr * M.ns * 8;
-		k_layout<<<grid_for(total, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
-		    M, st, d_b, stride64, row0, nr, row0);
-		e = cudaGetLastError();
+		e = cudaMemcpyAsync(d_b, b, (size_t)((m_loc + 63) / 64) * 8, cudaMemcpyHostToDevice, ctx->stream);
+	int ci = 0, used[2] = {0, 0};
+	for (Shard &h : sys->sh) {
+		const long long off = h.row_begin - base;
+		for (long long row0 = 0; e == cudaSuccess && row0 < h.M.m; row0 += chunk_rows) {
+			long long nr = std::min<long long>(chunk_rows, h.M.m - row0);
+			const int bi = stage[1] ? ci : 0;
+			/* the staging buffer is free once the layout kernel that read it is done */
+			if (used[bi]) e = cudaStreamWaitEvent(copy_stream, laid[bi], 0);
+			if (e == cudaSuccess)
+				e = cudaMemcpyAsync(stage[bi], A + (off + row0) * stride64, nr * row_bytes,
+				                    cudaMemcpyHostToDevice, copy_stream);
+			if (e == cudaSuccess) e = cudaEventRecord(copied[bi], copy_stream);
+			if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, copied[bi], 0);
+			if (e != cudaSuccess) break;
+			long long total = nr * h.M.ns * 8;
+			k_layout<<<grid_for(total, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
+			    h.M, stage[bi], d_b, stride64, row0, nr, off + row0);
+			e = cudaGetLastError();
+			if (e == cudaSuccess) e = cudaEventRecord(laid[bi], ctx->stream);
+			used[bi] = 1;
+			ci ^= 1;
+		}
 	}
 	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
 	if (e != cudaSuccess) rc = fail(ctx, GF2B200_ECUDA, "system_load_host: %s", cudaGetErrorString(e));
+	if (copy_stream) {
+		cudaStreamSynchronize(copy_stream);
+		cudaStreamDestroy(copy_stream);
+	}
 	cudaFree(stage[0]);
 	cudaFree(stage[1]);
 	cudaFree(d_b);
-	if (done[0]) cudaEventDestroy(done[0]);
-	if (done[1]) cudaEventDestroy(done[1]);
+	for (int i = 0; i < 2; i++) {
+		if (copied[i]) cudaEventDestroy(copied[i]);
+		if (laid[i]) cudaEventDestroy(laid[i]);
+	}
 	sys->eliminated = 0;
 	return rc;
 }
@@ -315,27 +487,154 @@ extern "C" int gf2b200_system_load_host(gf2b200_system *sys, const uint64_t *A, 
 extern "C" int gf2b200_system_generate(gf2b200_system *sys, uint64_t seed) {
 	if (!sys) return fail(nullptr, GF2B200_EINVAL, "NULL argument");
 	gf2b200_ctx *ctx = sys->ctx;
-	const Mat &M = sys->M;
 	CK(ctx, cudaSetDevice(ctx->device));
-	long long total = M.m * M.ns * 8;
-	k_generate<<<grid_for(total, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(M, seed, sys->row_begin);
-	/* x* goes through d_x (overwritten later by the solve) */
-	k_synth_xstar<<<(M.nw + 255) / 256, 256, 0, ctx->stream>>>(sys->d_x, M.nw, M.n, seed);
-	k_synth_dot<<<grid_for(M.m * 32, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
-	    M, seed, sys->row_begin, sys->d_x, 0, nullptr);
+	for (Shard &h : sys->sh) {
+		const Mat &M = h.M;
+		if (M.m == 0) continue;
+		long long total = M.m * M.ns * 8;
+		k_generate<<<grid_for(total, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(M, seed, h.row_begin);
+		/* x* goes through d_x (overwritten later by the solve) */
+		k_synth_xstar<<<(M.nw + 255) / 256, 256, 0, ctx->stream>>>(h.d_x, M.nw, M.n, seed);
+		k_synth_dot<<<grid_for(M.m * 32, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
+		    M, seed, h.row_begin, h.d_x, 0, nullptr);
+	}
 	CK(ctx, cudaGetLastError());
 	sys->eliminated = 0;
+	return GF2B200_OK;
+}
+
+/* all-gather over the system's shards: `bytes` of every shard's send buffer, in
+ * shard order, into every shard's recv buffer (NCCL, or device copies on a
+ * loopback context) */
+template <typename T, typename U>
+static int all_gather(gf2b200_system *sys, T *Shard::*send, U *Shard::*recv, size_t bytes, double *acct) {
+	gf2b200_ctx *ctx = sys->ctx;
+	if (ctx->nccl) {
+		Shard &h = sys->sh[0];
+		NK(ctx, g_nccl.AllGather(h.*send, h.*recv, bytes, ncclUint8, ctx->nccl, ctx->stream));
+	} else {
+		for (Shard &d : sys->sh)
+			for (Shard &s : sys->sh)
+				CK(ctx, cudaMemcpyAsync((char *)(d.*recv) + (size_t)s.index * bytes, s.*send, bytes,
+				                        cudaMemcpyDeviceToDevice, ctx->stream));
+	}
+	if (acct) *acct += (double)bytes * sys->sh.size();
+	return GF2B200_OK;
+}
+
+/* forward elimination of a one-shard system (single GPU) */
+static int forward_single(gf2b200_system *sys, long long *launches) {
+	gf2b200_ctx *ctx = sys->ctx;
+	Shard &h = sys->sh[0];
+	const Mat &M = h.M;
+	cudaStream_t st = ctx->stream;
+	const bool prof = ctx->profile != 0;
+	const int nw = M.nw;
+	k_extract_pc<<<grid_for(M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(M, 0, h.d_pc[0], 0);
+	(*launches)++;
+	const int apply_cap = ctx->n_sm * 4;
+	for (int w = 0; w < nw; w++) {
+		u64 colmask = ~0ULL;
+		if (w == nw - 1 && (M.n & 63)) colmask = (1ULL << (M.n & 63)) - 1;
+		u64 *pc_cur = h.d_pc[w & 1], *pc_next = h.d_pc[(w + 1) & 1];
+		k_select<<<1, SEL_THREADS, 0, st>>>(M, pc_cur, w, colmask, h.d_state, h.d_pd, h.d_hist_r,
+		                                    h.d_hist_pm);
+		int s0a = w >> 3;
+		k_apply<<<std::min(M.ns - s0a, apply_cap), 256, 0, st>>>(M, h.d_pd, h.d_ebuf, s0a);
+		if (prof) CK(ctx, cudaEventRecord(sys->ev[4 + 2 * w], st));
+		k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(M, h.d_pd, pc_cur, pc_next, h.d_ebuf, w,
+		                                                     (w + 1) >> 3);
+		if (prof) CK(ctx, cudaEventRecord(sys->ev[5 + 2 * w], st));
+		*launches += 3;
+	}
+	k_check<<<grid_for(M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(M, h.d_state);
+	(*launches)++;
+	return GF2B200_OK;
+}
+
+/* forward elimination of a row-sharded system (nccl or loopback) */
+static int forward_sharded(gf2b200_system *sys, long long *launches, double *xbytes) {
+	gf2b200_ctx *ctx = sys->ctx;
+	cudaStream_t st = ctx->stream;
+	const bool prof = ctx->profile != 0;
+	const int G = ctx->world;
+	const int nw = sys->sh[0].M.nw, ns = sys->sh[0].M.ns;
+	const int apply_cap = ctx->n_sm * 4;
+	for (Shard &h : sys->sh) {
+		k_extract_pc<<<grid_for(h.M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(h.M, 0, h.d_pc[0], 0);
+		(*launches)++;
+	}
+	for (int w = 0; w < nw; w++) {
+		u64 colmask = ~0ULL;
+		if (w == nw - 1 && (sys->n & 63)) colmask = (1ULL << (sys->n & 63)) - 1;
+		const int s0a = w >> 3, nsr = ns - s0a;
+		for (Shard &h : sys->sh)
+			k_select_local<<<1, SEL_THREADS, 0, st>>>(h.M, h.d_pc[w & 1], colmask, h.d_state, h.d_cand_send,
+			                                          h.d_selrow);
+		int rc = all_gather(sys, &Shard::d_cand_send, &Shard::d_cand_all, CAND_W * 8, xbytes);
+		if (rc) return rc;
+		for (Shard &h : sys->sh) {
+			k_elect<<<1, 32, 0, st>>>(h.d_cand_all, G, h.index, w, colmask, h.d_state, h.d_pd, h.d_dp,
+			                          h.d_selrow, h.d_pc[w & 1], h.d_hist_r, h.d_hist_pm, h.d_hist_owner);
+			k_pack<<<std::min(nsr, apply_cap), 256, 0, st>>>(h.M, h.d_dp, h.d_rows_send, s0a);
+		}
+		rc = all_gather(sys, &Shard::d_rows_send, &Shard::d_rows_all, (size_t)64 * nsr * 64, xbytes);
+		if (rc) return rc;
+		int li = 0;
+		for (Shard &h : sys->sh) {
+			k_apply_dist<<<std::min(nsr, apply_cap), 256, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_rows_all, h.d_ebuf,
+			                                                      s0a);
+			const bool ev = prof && li == 0;
+			if (ev) CK(ctx, cudaEventRecord(sys->ev[4 + 2 * w], st));
+			k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(h.M, h.d_pd, h.d_pc[w & 1],
+			                                                     h.d_pc[(w + 1) & 1], h.d_ebuf, w, (w + 1) >> 3);
+			if (ev) CK(ctx, cudaEventRecord(sys->ev[5 + 2 * w], st));
+			li++;
+		}
+		*launches += 5 * (long long)sys->sh.size();
+	}
+	for (Shard &h : sys->sh) {
+		k_check<<<grid_for(h.M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(h.M, h.d_state);
+		(*launches)++;
+	}
+	CK(ctx, cudaGetLastError());
+	return GF2B200_OK;
+}
+
+/* blocked back-substitution of the particular solution into every shard's d_x */
+static int backward(gf2b200_system *sys, long long *launches, double *xbytes) {
+	gf2b200_ctx *ctx = sys->ctx;
+	cudaStream_t st = ctx->stream;
+	const int nw = sys->sh[0].M.nw;
+	const bool sharded = ctx->world > 1;
+	const int nsp = (nw + BS_S - 1) / BS_S;
+	for (Shard &h : sys->sh) k_bs_init<<<(nw + 256) / 256, 256, 0, st>>>(h.d_x, nw);
+	for (int P = nsp - 1; P >= 0; --P) {
+		for (Shard &h : sys->sh)
+			k_bs_outer<<<BS_S * 64 * 32 / 256, 256, 0, st>>>(h.M, h.d_hist_r, h.d_hist_pm,
+			                                                sharded ? h.d_hist_owner : nullptr, h.index, h.d_x,
+			                                                h.d_slab, P);
+		if (sharded) {
+			int rc = all_gather(sys, &Shard::d_slab, &Shard::d_slab_all, (size_t)BS_S * 64 * BS_W * 8, xbytes);
+			if (rc) return rc;
+		}
+		for (Shard &h : sys->sh)
+			k_bs_inner<<<1, 1024, 0, st>>>(h.d_slab_all, h.d_hist_pm, sharded ? h.d_hist_owner : nullptr, h.d_x,
+			                               P, nw);
+		*launches += 2 * (long long)sys->sh.size();
+	}
+	CK(ctx, cudaGetLastError());
 	return GF2B200_OK;
 }
 
 extern "C" int gf2b200_system_eliminate(gf2b200_system *sys) {
 	if (!sys) return fail(nullptr, GF2B200_EINVAL, "NULL argument");
 	gf2b200_ctx *ctx = sys->ctx;
-	const Mat &M = sys->M;
 	cudaStream_t st = ctx->stream;
 	CK(ctx, cudaSetDevice(ctx->device));
-	const int nw = M.nw;
+	const int nw = sys->sh[0].M.nw, ns = sys->sh[0].M.ns;
 	const bool prof = ctx->profile != 0;
+	const bool sharded = ctx->world > 1;
 	size_t need_ev = 4 + (prof ? 2 * (size_t)nw : 0);
 	while (sys->ev.size() < need_ev) {
 		cudaEvent_t e;
@@ -344,45 +643,52 @@ extern "C" int gf2b200_system_eliminate(gf2b200_system *sys) {
 	}
 	cudaEvent_t ev_begin = sys->ev[0], ev_fwd = sys->ev[1], ev_end = sys->ev[2];
 	long long launches = 0;
+	double xbytes = 0;
 
 	CK(ctx, cudaEventRecord(ev_begin, st));
-	CK(ctx, cudaMemsetAsync(sys->d_state, 0, sizeof(SolverState), st));
-	k_extract_pc<<<grid_for(M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(M, 0, sys->d_pc[0], 0);
-	launches++;
-	const int apply_cap = ctx->n_sm * 4;
-	for (int w = 0; w < nw; w++) {
-		u64 colmask = ~0ULL;
-		if (w == nw - 1 && (M.n & 63)) colmask = (1ULL << (M.n & 63)) - 1;
-		u64 *pc_cur = sys->d_pc[w & 1], *pc_next = sys->d_pc[(w + 1) & 1];
-		k_select<<<1, SEL_THREADS, 0, st>>>(M, pc_cur, w, colmask, sys->d_state, sys->d_pd,
-		                                    sys->d_hist_r, sys->d_hist_pm);
-		int s0a = w >> 3;
-		k_apply<<<std::min(M.ns - s0a, apply_cap), 256, 0, st>>>(M, sys->d_pd, sys->d_ebuf, s0a);
-		if (prof) CK(ctx, cudaEventRecord(sys->ev[4 + 2 * w], st));
-		k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(M, sys->d_pd, pc_cur, pc_next,
-		                                                     sys->d_ebuf, w, (w + 1) >> 3);
-		if (prof) CK(ctx, cudaEventRecord(sys->ev[5 + 2 * w], st));
-		launches += 3;
-	}
-	k_check<<<grid_for(M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(M, sys->d_state);
-	launches++;
+	for (Shard &h : sys->sh) CK(ctx, cudaMemsetAsync(h.d_state, 0, sizeof(SolverState), st));
+	int rc = sharded ? forward_sharded(sys, &launches, &xbytes) : forward_single(sys, &launches);
+	if (rc) return rc;
 	CK(ctx, cudaEventRecord(ev_fwd, st));
-	size_t xs_bytes = (size_t)M.ns * 64;
-	if (xs_bytes > 200 * 1024) return fail(ctx, GF2B200_EINVAL, "n too large for the back-substitution kernel");
-	k_backsub<<<1, 1024, xs_bytes, st>>>(M, sys->d_hist_r, sys->d_hist_pm, nullptr, 1, sys->d_x);
-	launches++;
+	rc = backward(sys, &launches, &xbytes);
+	if (rc) return rc;
 	CK(ctx, cudaEventRecord(ev_end, st));
 	CK(ctx, cudaGetLastError());
 
-	sys->hist_r.resize(nw);
 	sys->hist_pm.resize(nw);
-	SolverState hs;
-	CK(ctx, cudaMemcpyAsync(sys->hist_r.data(), sys->d_hist_r, (size_t)nw * 8, cudaMemcpyDeviceToHost, st));
-	CK(ctx, cudaMemcpyAsync(sys->hist_pm.data(), sys->d_hist_pm, (size_t)nw * 8, cudaMemcpyDeviceToHost, st));
-	CK(ctx, cudaMemcpyAsync(&hs, sys->d_state, sizeof hs, cudaMemcpyDeviceToHost, st));
+	std::vector<SolverState> hs(sys->sh.size());
+	CK(ctx, cudaMemcpyAsync(sys->hist_pm.data(), sys->sh[0].d_hist_pm, (size_t)nw * 8, cudaMemcpyDeviceToHost, st));
+	if (sharded) {
+		sys->hist_owner.resize((size_t)nw * 64);
+		CK(ctx, cudaMemcpyAsync(sys->hist_owner.data(), sys->sh[0].d_hist_owner, (size_t)nw * 64,
+		                        cudaMemcpyDeviceToHost, st));
+	}
+	for (size_t l = 0; l < sys->sh.size(); l++) {
+		Shard &h = sys->sh[l];
+		h.hist_r.resize(nw);
+		CK(ctx, cudaMemcpyAsync(h.hist_r.data(), h.d_hist_r, (size_t)nw * 8, cudaMemcpyDeviceToHost, st));
+		CK(ctx, cudaMemcpyAsync(&hs[l], h.d_state, sizeof(SolverState), cudaMemcpyDeviceToHost, st));
+	}
 	CK(ctx, cudaStreamSynchronize(st));
-	sys->rank = hs.r;
-	sys->inconsistent = hs.inconsistent;
+	sys->rank = hs[0].r;
+	int bad = 0;
+	for (const SolverState &s : hs) bad |= s.inconsistent;
+	if (ctx->nccl) {
+		/* a shard with an active row "0 = 1" makes the whole system inconsistent */
+		int *d_flag = nullptr;
+		std::vector<int> flags(ctx->world, 0);
+		CK(ctx, cudaMalloc(&d_flag, sizeof(int) * (ctx->world + 1)));
+		cudaError_t e = cudaMemcpyAsync(d_flag + ctx->world, &bad, sizeof(int), cudaMemcpyHostToDevice, st);
+		ncclResult_t r = g_nccl.AllGather(d_flag + ctx->world, d_flag, sizeof(int), ncclUint8, ctx->nccl, st);
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(flags.data(), d_flag, sizeof(int) * ctx->world, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+		cudaFree(d_flag);
+		if (r != ncclSuccess) return fail(ctx, GF2B200_ENCCL, "ncclAllGather: %s", g_nccl.GetErrorString(r));
+		if (e != cudaSuccess) return fail(ctx, GF2B200_ECUDA, "flag exchange: %s", cudaGetErrorString(e));
+		for (int f : flags) bad |= f;
+	}
+	sys->inconsistent = bad;
 	sys->eliminated = 1;
 
 	gf2b200_stats &S = sys->stats;
@@ -395,22 +701,36 @@ extern "C" int gf2b200_system_eliminate(gf2b200_system *sys) {
 	CK(ctx, cudaEventElapsedTime(&ms, ev_fwd, ev_end));
 	S.ms_backward = ms;
 	S.kernel_launches = launches;
+	S.exchange_bytes = xbytes;
 	S.panels = nw;
 	S.rank = sys->rank;
-	S.m_local = M.m;
-	for (int w = 0; w < nw; w++) {
-		int k = __builtin_popcountll(sys->hist_pm[w]);
-		long long r1 = sys->hist_r[w] + k;
-		if (k == 0 || r1 >= M.m) continue;
-		double bytes = 2.0 * (double)(M.m - r1) * 64.0 * (double)(M.ns - ((w + 1) >> 3));
-		S.sweep_bytes += bytes;
-		S.sweep_launches++;
-		if (prof) {
-			CK(ctx, cudaEventElapsedTime(&ms, sys->ev[4 + 2 * w], sys->ev[5 + 2 * w]));
-			S.ms_sweep += ms;
-			if (ms > S.ms_sweep_max) {
-				S.ms_sweep_max = ms;
-				S.sweep_bytes_max = bytes;
+	S.m_local = gf2b200_system_local_rows(sys);
+	/* algorithmic sweep bytes of every local shard; the timed launches (profile
+	 * mode) are those of the first local shard */
+	for (size_t l = 0; l < sys->sh.size(); l++) {
+		const Shard &h = sys->sh[l];
+		for (int w = 0; w < nw; w++) {
+			const u64 pm = sys->hist_pm[w];
+			const int k = __builtin_popcountll(pm);
+			int mine = k;
+			if (sharded) {
+				mine = 0;
+				for (int j = 0; j < k; j++) mine += sys->hist_owner[(size_t)w * 64 + j] == h.index;
+			}
+			const long long r1 = h.hist_r[w] + mine;
+			if (k == 0 || r1 >= h.M.m) continue;
+			double bytes = 2.0 * (double)(h.M.m - r1) * 64.0 * (double)(ns - ((w + 1) >> 3));
+			S.sweep_bytes += bytes;
+			S.sweep_launches++;
+			if (prof && l == 0) {
+				CK(ctx, cudaEventElapsedTime(&ms, sys->ev[4 + 2 * w], sys->ev[5 + 2 * w]));
+				S.ms_sweep += ms;
+				S.sweep_bytes_timed += bytes;
+				S.sweep_launches_timed++;
+				if (ms > S.ms_sweep_max) {
+					S.ms_sweep_max = ms;
+					S.sweep_bytes_max = bytes;
+				}
 			}
 		}
 	}
@@ -429,7 +749,10 @@ extern "C" int gf2b200_system_result(gf2b200_system *sys, int mode, gf2b200_resu
 	memset(out, 0, sizeof *out);
 	if (mode != 0 && mode != 1) return fail(ctx, GF2B200_EINVAL, "Invalid mode");
 	if (!sys->eliminated) return fail(ctx, GF2B200_EINVAL, "system_result before system_eliminate");
-	const Mat &M = sys->M;
+	if (mode == 1 && ctx->world > 1)
+		return fail(ctx, GF2B200_EINVAL, "kernel basis (mode 1) is not available on a sharded system");
+	Shard &h = sys->sh[0];
+	const Mat &M = h.M;
 	const int nw = M.nw;
 	CK(ctx, cudaSetDevice(ctx->device));
 	out->rank = sys->rank;
@@ -443,7 +766,7 @@ extern "C" int gf2b200_system_result(gf2b200_system *sys, int mode, gf2b200_resu
 		gf2b200_result_free(out);
 		return fail(ctx, GF2B200_ENOMEM, "malloc");
 	}
-	CK(ctx, cudaMemcpyAsync(out->origin, sys->d_x, (size_t)nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(ctx, cudaMemcpyAsync(out->origin, h.d_x, (size_t)nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	long long q = 0;
 	for (int w = 0; w < nw; w++) {
 		u64 pm = sys->hist_pm[w];
@@ -465,6 +788,11 @@ extern "C" int gf2b200_system_result(gf2b200_system *sys, int mode, gf2b200_resu
 			gf2b200_result_free(out);
 			return fail(ctx, GF2B200_ENOMEM, "malloc basis");
 		}
+		size_t xs_bytes = (size_t)M.ns * 64;
+		if (xs_bytes > 200 * 1024) {
+			gf2b200_result_free(out);
+			return fail(ctx, GF2B200_EINVAL, "n too large for the kernel-basis back-substitution kernel");
+		}
 		long long *d_free = nullptr;
 		u64 *d_basis = nullptr;
 		/* batches bound the device buffer for huge nullities */
@@ -475,8 +803,8 @@ extern "C" int gf2b200_system_result(gf2b200_system *sys, int mode, gf2b200_resu
 			e = cudaMemcpyAsync(d_free, sigma.data() + r, (size_t)d * 8, cudaMemcpyHostToDevice, ctx->stream);
 		for (long long b0 = 0; e == cudaSuccess && b0 < d; b0 += batch) {
 			long long nb = std::min(batch, d - b0);
-			k_backsub<<<(unsigned)nb, 1024, (size_t)M.ns * 64, ctx->stream>>>(
-			    M, sys->d_hist_r, sys->d_hist_pm, d_free + b0, 0, d_basis);
+			k_backsub<<<(unsigned)nb, 1024, xs_bytes, ctx->stream>>>(M, h.d_hist_r, h.d_hist_pm, d_free + b0, 0,
+			                                                        d_basis);
 			e = cudaGetLastError();
 			if (e == cudaSuccess)
 				e = cudaMemcpyAsync(out->basis + b0 * nw, d_basis, (size_t)nb * nw * 8,
@@ -499,22 +827,24 @@ extern "C" int gf2b200_system_check_synthetic(gf2b200_system *sys, uint64_t seed
                                               int64_t *bad_rows) {
 	if (!sys || !x || !bad_rows) return fail(sys ? sys->ctx : nullptr, GF2B200_EINVAL, "NULL argument");
 	gf2b200_ctx *ctx = sys->ctx;
-	const Mat &M = sys->M;
+	const int nw = sys->sh[0].M.nw;
 	CK(ctx, cudaSetDevice(ctx->device));
 	u64 *d_v = nullptr, *d_xs = nullptr;
 	unsigned long long *d_cnt = nullptr;
 	unsigned long long cnt = 0;
-	cudaError_t e = cudaMalloc(&d_v, (size_t)M.nw * 8);
-	if (e == cudaSuccess) e = cudaMalloc(&d_xs, (size_t)M.nw * 8);
+	cudaError_t e = cudaMalloc(&d_v, (size_t)nw * 8);
+	if (e == cudaSuccess) e = cudaMalloc(&d_xs, (size_t)nw * 8);
 	if (e == cudaSuccess) e = cudaMalloc(&d_cnt, 8);
 	if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, 8, ctx->stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(d_v, x, (size_t)M.nw * 8, cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_v, x, (size_t)nw * 8, cudaMemcpyHostToDevice, ctx->stream);
 	if (e == cudaSuccess) {
 		/* A (x ^ x*) == 0  <=>  A x == b because b = A x* by construction */
-		k_synth_xstar<<<(M.nw + 255) / 256, 256, 0, ctx->stream>>>(d_xs, M.nw, M.n, seed);
-		k_xor_vec<<<(M.nw + 255) / 256, 256, 0, ctx->stream>>>(d_v, d_v, d_xs, M.nw);
-		k_synth_dot<<<grid_for(M.m * 32, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
-		    M, seed, sys->row_begin, d_v, 1, d_cnt);
+		k_synth_xstar<<<(nw + 255) / 256, 256, 0, ctx->stream>>>(d_xs, nw, sys->n, seed);
+		k_xor_vec<<<(nw + 255) / 256, 256, 0, ctx->stream>>>(d_v, d_v, d_xs, nw);
+		for (Shard &h : sys->sh)
+			if (h.M.m)
+				k_synth_dot<<<grid_for(h.M.m * 32, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
+				    h.M, seed, h.row_begin, d_v, 1, d_cnt);
 		e = cudaGetLastError();
 	}
 	if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream);
@@ -533,7 +863,7 @@ extern "C" int gf2b200_solve(gf2b200_ctx *ctx, const uint64_t *A, const uint64_t
 	if (!ctx || !A || !out) return fail(ctx, GF2B200_EINVAL, "NULL argument");
 	memset(out, 0, sizeof *out);
 	if (mode != 0 && mode != 1) return fail(ctx, GF2B200_EINVAL, "Invalid mode");
-	if (ctx->world != 1) return fail(ctx, GF2B200_EINVAL, "gf2b200_solve needs a single-GPU context");
+	if (ctx->nccl) return fail(ctx, GF2B200_EINVAL, "gf2b200_solve needs a single-process context");
 	gf2b200_system *sys = nullptr;
 	int rc = gf2b200_system_create(ctx, m, n, &sys);
 	if (rc) return rc;

@@ -1,0 +1,348 @@
+/*
+ * gf2b200_dist.cuh -- kernels of the row-sharded (multi-GPU) elimination and of
+ * the blocked back-substitution shared by the single- and multi-GPU paths.
+ *
+ * Sharding: shard g of G holds the contiguous global rows
+ * [g*m/G, (g+1)*m/G) in its own strip-major Mat; columns are never split, so all
+ * XOR traffic of the sweep stays in local HBM.  Per 64-column panel w:
+ *
+ *   k_select_local  each shard reduces ITS active rows' panel words to <= 64
+ *                   candidate rows (a basis of their span) and publishes the
+ *                   candidates' raw 64-bit panel words;
+ *   [exchange 1]    all-gather of the candidate words (G * 66 words);
+ *   k_elect         every shard runs the same deterministic election over the
+ *                   G*64 candidates (priority rotates with w so rows deplete
+ *                   evenly): the elected rows' pivot columns are the panel's
+ *                   GLOBAL column rank profile -- what _mzd_pluq reports in Q
+ *                   (reference _internal.c:433) -- because the
+ *                   union of the local bases spans the global active row space;
+ *   k_pack          owners copy their elected rows (trailing strips) to a send slab;
+ *   [exchange 2]    all-gather of the slabs: the "broadcast of each pivot row";
+ *   k_apply_dist    E = TB * Sel from the gathered rows -> ebuf (for the sweep);
+ *                   the shard that owned the j-th elected row stores E_j in place;
+ *   k_sweep         unchanged, on the local active rows.
+ *
+ * Back-substitution (k_bs_outer / k_bs_inner) is a blocked triangular solve over
+ * super-panels of BS_S panel words; see the comments at those kernels.
+ */
+#pragma once
+#include "gf2b200_kernels.cuh"
+
+namespace gf2b200 {
+
+#define CAND_W 66 /* words per shard in exchange 1: count, 64 panel words, pad */
+
+/* Per-shard description of its share of the current panel (written by k_elect). */
+struct DistPanel {
+	int my_cnt;        /* elected rows owned by this shard */
+	int my_row[64];    /* local row of my i-th elected row (before the moves) */
+	int my_slot[64];   /* candidate slot it is sent in */
+	int my_idx_of_j[64]; /* for E row j (pivot-column rank): index i among mine, or -1 */
+};
+
+/* ------------------------------------------------------------------------
+ * k_select_local: candidates of one shard for panel word w.
+ * cand[0] = count, cand[1 + l] = raw panel word of the l-th candidate row;
+ * selrow[l] = its local row.
+ * ---------------------------------------------------------------------- */
+__global__ void __launch_bounds__(SEL_THREADS, 1)
+k_select_local(Mat M, const u64 *__restrict__ pc, u64 colmask, const SolverState *st,
+               u64 *__restrict__ cand, int *__restrict__ selrow) {
+	__shared__ SelectSmem S;
+	const int tid = threadIdx.x;
+	if (tid < 64) {
+		S.B[tid] = 0;
+		S.TB[tid] = 0;
+		S.sel[tid] = -1;
+	}
+	if (tid == 0) {
+		S.pm = 0;
+		S.nsel = 0;
+	}
+	__syncthreads();
+	select_scan(S, pc, st->r_loc, M.m, colmask);
+	if (tid < 64) {
+		const int n = S.nsel;
+		cand[1 + tid] = (tid < n) ? (pc[S.sel[tid]] & colmask) : 0;
+		selrow[tid] = (tid < n) ? S.sel[tid] : -1;
+		if (tid == 0) {
+			cand[0] = (u64)n;
+			cand[65] = 0;
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------
+ * k_elect: global pivot election, one warp, identical on every shard.
+ * cand_all = G blocks of CAND_W words.  Candidate code = shard * 64 + slot.
+ * ---------------------------------------------------------------------- */
+__global__ void __launch_bounds__(32)
+k_elect(const u64 *__restrict__ cand_all, int G, int me, int w, u64 colmask, SolverState *st,
+        PanelDesc *pd, DistPanel *dp, const int *__restrict__ selrow, u64 *__restrict__ pc,
+        long long *hist_r, u64 *hist_pm, unsigned char *hist_owner) {
+	__shared__ u64 B[64], TB[64];
+	__shared__ int sel[64];
+	__shared__ int topsel[64], mv_src[64], mv_dst[64];
+	const int lane = threadIdx.x;
+	for (int c = lane; c < 64; c += 32) {
+		B[c] = 0;
+		TB[c] = 0;
+		sel[c] = -1;
+		topsel[c] = 0;
+	}
+	__syncwarp();
+	u64 pm = 0;
+	int nsel = 0;
+	for (int jj = 0; jj < G && pm != colmask; jj++) {
+		const int src = (w + jj) % G;
+		const u64 *cb = cand_all + (long long)src * CAND_W;
+		const int cnt = (int)cb[0];
+		for (int q0 = 0; q0 < cnt && pm != colmask; q0 += 32) {
+			const int q = q0 + lane;
+			const u64 v = (q < cnt) ? cb[1 + q] : 0;
+			warp0_insert(B, TB, sel, pm, nsel, colmask, v, 0, src * 64 + q, lane);
+		}
+	}
+	__syncwarp();
+	const int k = nsel;
+	const long long r_loc = st->r_loc;
+	for (int c = lane; c < 64; c += 32) {
+		pd->TB[c] = ((pm >> c) & 1) ? TB[c] : 0;
+		pd->sel[c] = sel[c];
+		hist_owner[(long long)w * 64 + c] = (c < k) ? (unsigned char)(sel[c] >> 6) : 0xFF;
+	}
+	/* my share, in election order */
+	int my_cnt = 0;
+	for (int h = 0; h < 2; h++) {
+		const int j = lane + 32 * h;
+		const bool mine = (j < k) && ((sel[j] >> 6) == me);
+		const unsigned bal = __ballot_sync(0xffffffffu, mine);
+		const int i = my_cnt + __popc(bal & ((1u << lane) - 1));
+		if (mine) {
+			dp->my_row[i] = selrow[sel[j] & 63];
+			dp->my_slot[i] = sel[j] & 63;
+			dp->my_idx_of_j[j] = i;
+		} else {
+			dp->my_idx_of_j[j] = -1;
+		}
+		my_cnt += __popc(bal);
+	}
+	__syncwarp();
+	__threadfence_block();
+	/* local rows r_loc .. r_loc+my_cnt-1 become this shard's echelon rows */
+	for (int i = lane; i < my_cnt; i += 32) {
+		const int row = dp->my_row[i];
+		if (row < r_loc + my_cnt) topsel[row - (int)r_loc] = 1;
+	}
+	__syncwarp();
+	int nvac = 0, ndis = 0;
+	for (int h = 0; h < 2; h++) {
+		const int i = lane + 32 * h;
+		const bool vac = (i < my_cnt) && (dp->my_row[i] >= r_loc + my_cnt);
+		const unsigned bv = __ballot_sync(0xffffffffu, vac);
+		if (vac) mv_dst[nvac + __popc(bv & ((1u << lane) - 1))] = dp->my_row[i];
+		nvac += __popc(bv);
+		const bool dis = (i < my_cnt) && !topsel[i];
+		const unsigned bd = __ballot_sync(0xffffffffu, dis);
+		if (dis) mv_src[ndis + __popc(bd & ((1u << lane) - 1))] = (int)r_loc + i;
+		ndis += __popc(bd);
+	}
+	__syncwarp();
+	u64 tmpv[2];
+	for (int h = 0; h < 2; h++) {
+		const int q = lane + 32 * h;
+		tmpv[h] = (q < ndis) ? pc[mv_src[q]] : 0;
+	}
+	__syncwarp();
+	for (int h = 0; h < 2; h++) {
+		const int q = lane + 32 * h;
+		if (q < ndis) {
+			pc[mv_dst[q]] = tmpv[h];
+			pd->mv_src[q] = mv_src[q];
+			pd->mv_dst[q] = mv_dst[q];
+		}
+	}
+	if (lane == 0) {
+		dp->my_cnt = my_cnt;
+		pd->r = r_loc;
+		pd->r1 = r_loc + my_cnt;
+		pd->k = k;
+		pd->nmove = ndis;
+		pd->pm = pm;
+		st->r += k;
+		st->r_loc = r_loc + my_cnt;
+		hist_r[w] = r_loc;
+		hist_pm[w] = pm;
+	}
+}
+
+/* my elected rows, strips [s0, ns) -> send slab [slot][strip - s0][64 B] */
+__global__ void __launch_bounds__(256)
+k_pack(Mat M, const DistPanel *__restrict__ dp, uint4 *__restrict__ rows_send, int s0) {
+	const int cnt = dp->my_cnt;
+	const int tid = threadIdx.x, rr = tid >> 2, ch = tid & 3;
+	if (rr >= cnt) return;
+	const int row = dp->my_row[rr], slot = dp->my_slot[rr];
+	const int nsr = M.ns - s0;
+	const uint4 *mb = reinterpret_cast<const uint4 *>(M.base);
+	for (int s = s0 + blockIdx.x; s < M.ns; s += gridDim.x)
+		rows_send[((long long)slot * nsr + (s - s0)) * 4 + ch] = mb[((long long)s * M.mp + row) * 4 + ch];
+}
+
+/* k_apply for gathered rows: rows_all = [G*64 codes][ns - s0][64 B] */
+__global__ void __launch_bounds__(256)
+k_apply_dist(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restrict__ dp,
+             const uint4 *__restrict__ rows_all, uint4 *__restrict__ ebuf, int s0) {
+	__shared__ uint4 Sel[64][4];
+	__shared__ uint4 Dis[64][4];
+	__shared__ u64 sTB[64];
+	__shared__ int scode[64], ssrc[64], sdst[64], smyidx[64];
+	const int k = pd->k;
+	if (k == 0) return;
+	const int tid = threadIdx.x, rr = tid >> 2, ch = tid & 3;
+	const long long r = pd->r;
+	const int nmove = pd->nmove;
+	const u64 pm = pd->pm;
+	if (tid < 64) {
+		sTB[tid] = pd->TB[tid];
+		scode[tid] = pd->sel[tid];
+		ssrc[tid] = pd->mv_src[tid];
+		sdst[tid] = pd->mv_dst[tid];
+		smyidx[tid] = dp->my_idx_of_j[tid];
+	}
+	__syncthreads();
+	uint4 *mb = reinterpret_cast<uint4 *>(M.base);
+	const int nsr = M.ns - s0;
+	const bool ispiv = (pm >> rr) & 1;
+	const int jrank = __popcll(pm & ((1ULL << rr) - 1));
+	const int myi = ispiv ? smyidx[jrank] : -1;
+	for (int s = s0 + blockIdx.x; s < M.ns; s += gridDim.x) {
+		const long long sb = (long long)s * M.mp;
+		uint4 z = make_uint4(0, 0, 0, 0);
+		Sel[rr][ch] = (rr < k) ? rows_all[((long long)scode[rr] * nsr + (s - s0)) * 4 + ch] : z;
+		if (rr < nmove) Dis[rr][ch] = mb[(sb + ssrc[rr]) * 4 + ch];
+		__syncthreads();
+		uint4 acc = z;
+		u64 t = sTB[rr];
+		while (t) {
+			int l = __ffsll((long long)t) - 1;
+			t &= t - 1;
+			xor4(acc, Sel[l][ch]);
+		}
+		ebuf[(long long)s * 256 + rr * 4 + ch] = acc;
+		if (myi >= 0) mb[(sb + r + myi) * 4 + ch] = acc;
+		if (rr < nmove) mb[(sb + sdst[rr]) * 4 + ch] = Dis[rr][ch];
+		__syncthreads();
+	}
+}
+
+/* ------------------------------------------------------------------------
+ * Blocked back-substitution of the particular solution (free variables 0;
+ * reference _mzd_pluq_solve_left, _internal.c:440-454).
+ *
+ * The echelon rows of panel w (E_j, RREF inside the panel word) sit at local rows
+ * hist_r[w] + i of their owner shard.  Super-panel P covers panel words
+ * [P*BS_S, (P+1)*BS_S).  From the last super-panel to the first:
+ *   k_bs_outer  (all SMs) for every echelon row of P: y = <row[words beyond P], x>
+ *               with x[nw] = 1 standing for the b column, and a copy of the row's
+ *               BS_S words inside P  ->  slab[(wp*64 + j)][BS_W]
+ *   [exchange]  all-gather of the slabs (multi-GPU only)
+ *   k_bs_inner  (one CTA, identical on every shard) solves the BS_S-word
+ *               triangular block panel by panel and writes x[P*BS_S ..].
+ * ---------------------------------------------------------------------- */
+#define BS_S 32 /* panel words per super-panel (4 strips) */
+#define BS_W 40 /* slab row: BS_S words, then y at [BS_S], padding */
+
+__global__ void __launch_bounds__(256)
+k_bs_outer(Mat M, const long long *__restrict__ hist_r, const u64 *__restrict__ hist_pm,
+           const unsigned char *__restrict__ hist_owner, int me, const u64 *__restrict__ x,
+           u64 *__restrict__ slab, int P) {
+	const int lane = threadIdx.x & 31;
+	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; /* (wp, j) */
+	if (gw >= BS_S * 64) return;
+	const int wp = gw >> 6, j = gw & 63;
+	const int w = P * BS_S + wp;
+	u64 *out = slab + (long long)gw * BS_W;
+	long long row = -1;
+	if (w < M.nw) {
+		const u64 pm = hist_pm[w];
+		if (j < __popcll(pm)) {
+			if (!hist_owner) {
+				row = hist_r[w] + j;
+			} else if (hist_owner[(long long)w * 64 + j] == me) {
+				int i = 0;
+				for (int jj = 0; jj < j; jj++) i += (hist_owner[(long long)w * 64 + jj] == me);
+				row = hist_r[w] + i;
+			}
+		}
+	}
+	if (row < 0) {
+		for (int l = lane; l < BS_W; l += 32) out[l] = 0;
+		return;
+	}
+	/* outer part: strips beyond the super-panel, 8 lanes per 64-byte piece */
+	const int wl = lane & 7, so = lane >> 3;
+	const u64 *rowp = M.base + row * 8 + wl;
+	u64 acc = 0;
+	for (int s = (P + 1) * (BS_S / 8) + so; s < M.ns; s += 4) {
+		const int wd = s * 8 + wl;
+		if (wd <= M.nw) acc ^= rowp[(long long)s * M.mp * 8] & x[wd];
+	}
+	int par = __popcll(acc) & 1;
+	par = __reduce_xor_sync(0xffffffffu, par);
+	/* inner part: the row's words inside the super-panel.  The b word (index nw,
+	 * "unknown" fixed to 1) may fall inside the last super-panel: fold it into y. */
+	{
+		const int wd = P * BS_S + lane;
+		const u64 v = (wd <= M.nw) ? M.base[widx(M, row, wd)] : 0;
+		const int bpar = (wd == M.nw) ? (int)(v & 1) : 0;
+		par ^= __reduce_or_sync(0xffffffffu, bpar);
+		out[lane] = (wd < M.nw) ? v : 0;
+	}
+	if (lane == 0) out[BS_S] = (u64)(par & 1);
+	if (lane > 0 && lane < BS_W - BS_S) out[BS_S + lane] = 0;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+k_bs_inner(const u64 *__restrict__ slab_all, const u64 *__restrict__ hist_pm,
+           const unsigned char *__restrict__ hist_owner, u64 *__restrict__ x, int P, int nw) {
+	__shared__ u64 xs[BS_S];
+	__shared__ unsigned long long newbits;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid < BS_S) xs[tid] = 0;
+	if (tid == 0) newbits = 0;
+	__syncthreads();
+	const int nwp = min(BS_S, nw - P * BS_S);
+	for (int wp = nwp - 1; wp >= 0; --wp) {
+		const int w = P * BS_S + wp;
+		const u64 pm = hist_pm[w];
+		const int k = __popcll(pm);
+		for (int j = warp; j < k; j += 32) {
+			const int src = hist_owner ? hist_owner[(long long)w * 64 + j] : 0;
+			const u64 *row = slab_all + ((long long)src * (BS_S * 64) + wp * 64 + j) * BS_W;
+			u64 a = (lane > wp) ? (row[lane] & xs[lane]) : 0;
+			int par = __popcll(a) & 1;
+			par = __reduce_xor_sync(0xffffffffu, par) ^ (int)(row[BS_S] & 1);
+			if (lane == 0 && par) {
+				u64 t = pm;
+				for (int q = 0; q < j; q++) t &= t - 1;
+				atomicOr(&newbits, t & (~t + 1));
+			}
+		}
+		__syncthreads();
+		if (tid == 0) {
+			xs[wp] = newbits;
+			newbits = 0;
+		}
+		__syncthreads();
+	}
+	if (tid < nwp) x[P * BS_S + tid] = xs[tid];
+}
+
+/* x[0..nw) = 0, x[nw] = 1 (the b column's "unknown") */
+__global__ void k_bs_init(u64 *x, int nw) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i <= nw) x[i] = (i == nw) ? 1 : 0;
+}
+
+} /* namespace gf2b200 */

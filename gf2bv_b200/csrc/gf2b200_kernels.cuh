@@ -51,6 +51,7 @@ struct Mat {
 /* Device-resident description of the current panel (written by k_select). */
 struct PanelDesc {
 	long long r;     /* echelon rows before this panel */
+	long long r1;    /* first active (not yet pivot) row after this panel */
 	int k;           /* pivots found in this panel */
 	int nmove;       /* displaced rows to relocate */
 	u64 pm;          /* pivot column mask within the panel word */
@@ -61,7 +62,8 @@ struct PanelDesc {
 };
 
 struct SolverState {
-	long long r;     /* current rank == first active row */
+	long long r;     /* current (global) rank */
+	long long r_loc; /* first active row of this shard (== r on a single GPU) */
 	int inconsistent;
 	int pad;
 };
@@ -360,10 +362,12 @@ k_select(Mat M, u64 *__restrict__ pc, int w, u64 colmask, SolverState *st, Panel
 	}
 	if (lane == 0) {
 		pd->r = r;
+		pd->r1 = r + k;
 		pd->k = k;
 		pd->nmove = ndis;
 		pd->pm = pm;
 		st->r = r + k;
+		st->r_loc = r + k;
 		hist_r[w] = r;
 		hist_pm[w] = pm;
 	}
@@ -422,19 +426,33 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
 
 /* ------------------------------------------------------------------------
  * k_sweep: the HBM-bound row-XOR sweep.
- *   rows [r1, m) x strips [s0, ns):  piece ^= XOR_g T[g][byte g of (pc_cur[row] & pm)]
+ *   rows [r1, m) x strips [s0, ns):  piece ^= XOR_g T_g[field g of (pc_cur[row] & pm)]
  * Persistent grid (1 CTA of 1024 threads per SM); work units of 1024 rows x one
  * strip are dealt out contiguously in strip-major order so a CTA rebuilds its
  * tables only when it crosses into a new strip.
- * Shared memory: T[8][256][4] uint4 (128 KiB) | T4[8][2][16][4] (16 KiB) |
- * E[64][4] (4 KiB, filled by cp.async.bulk + mbarrier) | mbarrier.
+ *
+ * Four-Russians tables, laid out for conflict-free 128-bit lookups.  A lookup
+ * wavefront is a quarter-warp: 2 rows x 4 chunks of 16 B.  With plain 64-byte
+ * entries the two rows collide whenever their indices have equal parity (ncu,
+ * profiles/r01a: 33% of all shared wavefronts were such replays and the l1tex
+ * data pipe, not HBM, was the limiter).  Here every entry lives in a 128-byte
+ * line holding the SAME 64 bytes twice; the even row of the pair reads the low
+ * half, the odd row the high half, so the 8 threads always cover all 32 banks.
+ * The duplicated storage is paid for by splitting the 64 panel columns into
+ * eight 7-bit fields (128 lines each) plus one 8-bit field (256 lines):
+ * 9 lookups per 16 B instead of 8, all single-wavefront.
+ *
+ * Shared memory: TD[1280 lines][2 halves][4] uint4 (160 KiB) | P[224][4] partial
+ * tables (14 KiB) | E[64][4] (4 KiB, filled by cp.async.bulk + mbarrier) | mbarrier.
  * The CTA that updates the strip holding word w+1 also emits the dense copy of
  * that word column (pc_next) for the next panel's pivot search.
  * ---------------------------------------------------------------------- */
 #define SWEEP_THREADS 1024
 #define SWEEP_U 4
 #define SWEEP_RU (SWEEP_THREADS / 4 * SWEEP_U) /* rows per unit */
-#define SWEEP_SMEM (8 * 256 * 4 * 16 + 8 * 2 * 16 * 4 * 16 + 64 * 4 * 16 + 16)
+#define SWEEP_LINES (8 * 128 + 256)
+#define SWEEP_PARTS (8 * 24 + 32)
+#define SWEEP_SMEM (SWEEP_LINES * 128 + SWEEP_PARTS * 64 + 64 * 64 + 16)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) {
 	return (unsigned)__cvta_generic_to_shared(p);
@@ -469,18 +487,60 @@ __device__ __forceinline__ void xor4(uint4 &a, const uint4 &b) {
 	a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w;
 }
 
+/* Builds TD from the pivot-row tile E (64 columns x 64 B).  All SWEEP_THREADS
+ * threads; two __syncthreads inside, one more needed by the caller before use. */
+__device__ __forceinline__ void sweep_build_tables(uint4 *TD, uint4 *P, const uint4 *E, int tid) {
+	/* partial tables: field g < 8 (columns 7g..7g+6): 8 entries over its low 3
+	 * columns, 16 over its high 4; field 8 (columns 56..63): 16 + 16 */
+	if (tid < SWEEP_PARTS * 4) {
+		const int id = tid >> 2, ch = tid & 3;
+		int col0, e;
+		if (id < 192) {
+			const int g = id / 24, r = id - g * 24;
+			if (r < 8) { col0 = 7 * g; e = r; }
+			else { col0 = 7 * g + 3; e = r - 8; }
+		} else {
+			const int r = id - 192;
+			col0 = 56 + (r & 16 ? 4 : 0);
+			e = r & 15;
+		}
+		uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll
+		for (int b = 0; b < 4; b++)
+			if ((e >> b) & 1) xor4(acc, E[(col0 + b) * 4 + ch]);
+		P[tid] = acc;
+	}
+	__syncthreads();
+	/* full tables, both halves of each line: item = (line, half, chunk) */
+	for (int it = tid; it < SWEEP_LINES * 8; it += SWEEP_THREADS) {
+		const int L = it >> 3, ch = it & 3;
+		uint4 a, b;
+		if (L < 1024) {
+			const int g = L >> 7, e = L & 127;
+			a = P[(g * 24 + (e & 7)) * 4 + ch];
+			b = P[(g * 24 + 8 + (e >> 3)) * 4 + ch];
+		} else {
+			const int e = L - 1024;
+			a = P[(192 + (e & 15)) * 4 + ch];
+			b = P[(208 + (e >> 4)) * 4 + ch];
+		}
+		xor4(a, b);
+		TD[it] = a;
+	}
+}
+
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
 k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
         u64 *__restrict__ pc_next, const uint4 *__restrict__ ebuf, int w, int s0) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	uint4 *T = reinterpret_cast<uint4 *>(smem_raw);
-	uint4 *T4 = T + 8 * 256 * 4;
-	uint4 *E = T4 + 8 * 2 * 16 * 4;
+	uint4 *TD = reinterpret_cast<uint4 *>(smem_raw);
+	uint4 *P = TD + SWEEP_LINES * 8;
+	uint4 *E = P + SWEEP_PARTS * 4;
 	u64 *bar = reinterpret_cast<u64 *>(E + 64 * 4);
 
 	const int tid = threadIdx.x;
 	const int k = pd->k;
-	const long long r1 = pd->r + k;
+	const long long r1 = pd->r1;
 	const long long m = M.m;
 	if (r1 >= m) return;
 	const int wn = w + 1; /* next panel word (or the b word): always exists */
@@ -509,7 +569,8 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 	const int ch = tid & 3, rl = tid >> 2;
 	const int nch = (wn & 7) >> 1; /* chunk holding word wn inside its strip */
 	uint4 *mb = reinterpret_cast<uint4 *>(M.base);
-	const uint4 *Tc = T + ch;
+	/* this thread's half of every line: rows alternate halves inside a quarter-warp */
+	const unsigned char *Tb = reinterpret_cast<const unsigned char *>(TD + (rl & 1) * 4 + ch);
 
 	for (long long u = u0; u < u1; ++u) {
 		const int s = s0 + (int)(u / nchunks);
@@ -522,25 +583,7 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 			}
 			mbar_wait(bar, phase);
 			phase ^= 1;
-			{ /* 16-entry half tables: tid = ((g*2+h)*16+e)*4+ch */
-				const int gh = tid >> 6, e = (tid >> 2) & 15;
-				uint4 acc = make_uint4(0, 0, 0, 0);
-#pragma unroll
-				for (int b = 0; b < 4; b++)
-					if ((e >> b) & 1) xor4(acc, E[(gh * 4 + b) * 4 + ch]);
-				T4[tid] = acc;
-			}
-			__syncthreads();
-			{
-				const int idx = tid >> 2;
-#pragma unroll
-				for (int g = 0; g < 8; g++) {
-					uint4 a = T4[((g * 2 + 0) * 16 + (idx & 15)) * 4 + ch];
-					uint4 b = T4[((g * 2 + 1) * 16 + (idx >> 4)) * 4 + ch];
-					xor4(a, b);
-					T[(g * 256 + idx) * 4 + ch] = a;
-				}
-			}
+			sweep_build_tables(TD, P, E, tid);
 			__syncthreads();
 			cur = s;
 		}
@@ -565,15 +608,20 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 		for (int q = 0; q < SWEEP_U; q++) {
 			if (!act[q]) continue;
 			const unsigned lo = (unsigned)cf[q], hi = (unsigned)(cf[q] >> 32);
+			const unsigned mid = __funnelshift_r(lo, hi, 28);
 			uint4 v = d[q];
-			xor4(v, Tc[(0 * 256 + (lo & 255)) * 4]);
-			xor4(v, Tc[(1 * 256 + ((lo >> 8) & 255)) * 4]);
-			xor4(v, Tc[(2 * 256 + ((lo >> 16) & 255)) * 4]);
-			xor4(v, Tc[(3 * 256 + (lo >> 24)) * 4]);
-			xor4(v, Tc[(4 * 256 + (hi & 255)) * 4]);
-			xor4(v, Tc[(5 * 256 + ((hi >> 8) & 255)) * 4]);
-			xor4(v, Tc[(6 * 256 + ((hi >> 16) & 255)) * 4]);
-			xor4(v, Tc[(7 * 256 + (hi >> 24)) * 4]);
+			/* byte offset of a line = 128 * (field base + field value) */
+#define TLOOK(off) (*reinterpret_cast<const uint4 *>(Tb + (off)))
+			xor4(v, TLOOK(0 * 16384 + ((lo << 7) & 0x3F80u)));
+			xor4(v, TLOOK(1 * 16384 + (lo & 0x3F80u)));
+			xor4(v, TLOOK(2 * 16384 + ((lo >> 7) & 0x3F80u)));
+			xor4(v, TLOOK(3 * 16384 + ((lo >> 14) & 0x3F80u)));
+			xor4(v, TLOOK(4 * 16384 + ((mid << 7) & 0x3F80u)));
+			xor4(v, TLOOK(5 * 16384 + ((hi << 4) & 0x3F80u)));
+			xor4(v, TLOOK(6 * 16384 + ((hi >> 3) & 0x3F80u)));
+			xor4(v, TLOOK(7 * 16384 + ((hi >> 10) & 0x3F80u)));
+			xor4(v, TLOOK(8 * 16384 + ((hi >> 17) & 0x7F80u)));
+#undef TLOOK
 			p[(long long)(SWEEP_THREADS / 4) * q * 4] = v;
 			if (force && ch == nch) {
 				long long row = row0 + (SWEEP_THREADS / 4) * q;
@@ -586,7 +634,7 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 /* any active row (i >= rank) with b = 1 makes the system inconsistent
  * (_mzd_pluq_solve_left's check, _internal.c:440-446 -> None) */
 __global__ void k_check(Mat M, SolverState *st) {
-	const long long r = st->r;
+	const long long r = st->r_loc;
 	int bad = 0;
 	for (long long i = r + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M.m;
 	     i += (long long)gridDim.x * blockDim.x)

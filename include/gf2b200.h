@@ -70,6 +70,8 @@ typedef struct {
 	int64_t m_local;        /* rows held by this rank */
 	double ms_sweep_max;    /* profile mode: the longest single sweep and its bytes */
 	double sweep_bytes_max;
+	double sweep_bytes_timed;     /* profile mode: algorithmic bytes of the launches in ms_sweep */
+	int64_t sweep_launches_timed; /* (a loopback context times its first shard only) */
 } gf2b200_stats;
 
 int gf2b200_abi_version(void);
@@ -82,6 +84,11 @@ int gf2b200_create(gf2b200_ctx **out, int device);
 int gf2b200_nccl_unique_id(void *out_id128);
 int gf2b200_create_dist(gf2b200_ctx **out, int device, int rank, int world,
                         const void *nccl_id128);
+/* Loopback context: `world` row shards on ONE device in this process; the
+ * exchanges of the sharded algorithm become device copies.  Same kernels and
+ * control flow as the NCCL kind -- used to parity-test the sharded path on one
+ * GPU.  Systems of such a context take the WHOLE matrix in system_load_*. */
+int gf2b200_create_shards(gf2b200_ctx **out, int device, int world);
 void gf2b200_destroy(gf2b200_ctx *ctx);
 const char *gf2b200_last_error(const gf2b200_ctx *ctx);
 
@@ -107,7 +114,8 @@ void gf2b200_result_free(gf2b200_result *res);
 
 /* ---- device-resident systems -------------------------------------------- */
 /* m, n are GLOBAL sizes; with a dist context each rank holds rows
- * [rank*m/world, (rank+1)*m/world) of the global system. */
+ * [rank*m/world, (rank+1)*m/world) of the global system.  On a sharded system
+ * (dist or loopback) system_result supports mode 0 only. */
 int gf2b200_system_create(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2b200_system **out);
 void gf2b200_system_destroy(gf2b200_system *sys);
 int64_t gf2b200_system_local_rows(const gf2b200_system *sys);
