@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- GF(2) n x n echelonize throughput (bit-ops/s) on B200 vs the CPU path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n SIZE]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size N]
 
 A "step" is one full solve (forward elimination with 64-column panels, consistency
 check, back-substitution of the particular solution) of the dense synthetic system
@@ -338,7 +338,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--size", dest="n", type=int, default=0, help="matrix size n (default 131072 at 1 GPU, 524288 sharded)")
     ap.add_argument("--sample-n", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
