@@ -104,43 +104,20 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- host inputs for e2e
-def host_system_pinned(n: int, seed: int):
-    """The synthetic system in PINNED host memory (numpy views of torch pinned tensors)."""
+def host_rows_pinned(n: int, seed: int, r0: int, r1: int):
+    """Rows [r0, r1) of the synthetic system in PINNED host memory (numpy views of torch
+    pinned tensors), filled by the library's host-side workload generator."""
     import numpy as np
     import torch
 
+    from gf2bv_b200 import _shim
+
     nw = (n + 63) // 64
-    tA = torch.empty((n, nw), dtype=torch.int64, pin_memory=True)
-    tb = torch.zeros(((n + 63) // 64,), dtype=torch.int64, pin_memory=True)
-    A = tA.numpy().view(np.uint64)
+    tA = torch.empty((max(r1 - r0, 1), nw), dtype=torch.int64, pin_memory=True)
+    tb = torch.zeros(((r1 - r0 + 63) // 64 + 1,), dtype=torch.int64, pin_memory=True)
+    A = tA.numpy().view(np.uint64)[: r1 - r0]
     b = tb.numpy().view(np.uint64)
-
-    def mix(z):
-        z ^= z >> np.uint64(30); z *= np.uint64(0xBF58476D1CE4E5B9)
-        z ^= z >> np.uint64(27); z *= np.uint64(0x94D049BB133111EB)
-        z ^= z >> np.uint64(31)
-        return z
-
-    with np.errstate(over="ignore"):
-        phi = np.uint64(PHI)
-        x = mix(np.uint64(seed ^ 0xB200) + phi * np.arange(1, nw + 1, dtype=np.uint64))
-        tail = np.uint64((1 << (n & 63)) - 1) if n & 63 else None
-        if tail is not None:
-            x[-1] &= tail
-        rows_per = max(1, (32 << 20) // (nw * 8))
-        bbits = np.zeros(((n + 63) // 64) * 64, dtype=np.uint8)
-        wi = np.arange(1, nw + 1, dtype=np.uint64)
-        for r0 in range(0, n, rows_per):
-            r1 = min(n, r0 + rows_per)
-            idx = (np.arange(r0, r1, dtype=np.uint64)[:, None] * np.uint64(nw)) + wi[None, :]
-            blk = mix(np.uint64(seed) + phi * idx)
-            if tail is not None:
-                blk[:, -1] &= tail
-            A[r0:r1] = blk
-            acc = np.bitwise_xor.reduce(blk & x[None, :], axis=1)
-            par = np.unpackbits(acc.view(np.uint8).reshape(-1, 8), axis=1).sum(axis=1) & 1
-            bbits[r0:r1] = par
-        b[:] = np.packbits(bbits, bitorder="little").view(np.uint64)
+    _shim.synth_host(A, b, r0, n, seed)
     return tA, tb, A, b
 
 
@@ -196,7 +173,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
 
-    from gf2bv_b200 import _shim
+    from gf2bv_b200 import _dist, _shim
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- gf2bv_b200 has no CPU fallback")
@@ -205,11 +182,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     seed = 1
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt = torch.frombuffer(bytearray(_shim.Context.nccl_unique_id()), dtype=torch.uint8).cuda()
-        dist.broadcast(idt, 0)
-        ctx = _shim.Context(local_rank, rank, world, bytes(idt.cpu().numpy().tobytes()))
+        uid = _dist.broadcast_bytes(_shim.Context.nccl_unique_id() if rank == 0 else None, 128, 0)
+        ctx = _shim.Context(local_rank, rank, world, uid)
     else:
         ctx = _shim.Context(local_rank)
 
@@ -241,17 +215,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     barrier()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    tot_ms = float(sum(ms))
-    if world > 1:
-        t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tot_ms = float(t.item())
+    tot_ms = _dist.all_max(float(sum(ms)))  # device time, max over ranks
     res = sysm.result(0)
-    bad = sysm.check_synthetic(seed, res.origin) if res.status == 0 else -1
-    if world > 1:
-        t = torch.tensor([bad], dtype=torch.int64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        bad = int(t.item())
+    bad = _dist.all_sum(sysm.check_synthetic(seed, res.origin) if res.status == 0 else 1)
     if res.status != 0 or bad != 0:
         raise SystemExit(f"bench.py: solution check failed (status {res.status}, bad rows {bad})")
     value = steps * work(n) / (tot_ms / 1e3)
@@ -287,24 +253,42 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                            "GBs": stp["sweep_bytes_max"] / stp["ms_sweep_max"] / 1e6 if stp["ms_sweep_max"] else None},
     }
 
-    # ---- e2e through the C-ABI host-buffer call (N = 1; sharded runs load per-rank rows)
+    # ---- e2e: the same solve from HOST (pinned) buffers, copies inside the timed region.
+    # N = 1: one gf2b200_solve() call -- what the extension's m4ri_solve makes in place of M4RI.
+    # N > 1: every rank loads ITS rows from its host buffer (system_load_host), then
+    # eliminate + result; wall clock between barriers (= max over ranks).
     e2e = None
-    if world == 1 and not args.no_e2e:
-        tA, tb, A, b = host_system_pinned(n, seed)
-        e_steps = steps if steps <= 3 else 3
-        ctx.solve(A, b, n, 0)  # warm-up (allocations, pinned mappings)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            r = ctx.solve(A, b, n, 0)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        assert r.status == 0 and np.array_equal(r.origin, res.origin)
-        e2e = {"value": e_steps * work(n) / dt, "unit": UNIT, "steps": e_steps, "ms_per_step": 1e3 * dt / e_steps,
-               "h2d_bytes_per_step": int(A.nbytes + b.nbytes),
-               "d2h_bytes_per_step": int(res.origin.nbytes + 2 * 8 * ((n + 63) // 64) + 16),
-               "api": "gf2b200_solve(ctx, A_host_pinned, b_host, m, n, stride64, mode=0, &result)"}
-        del tA, tb
+    if not args.no_e2e:
+        try:
+            r0, r1 = _dist.row_range(n, rank, world)
+            tA, tb, A, b = host_rows_pinned(n, seed, r0, r1)
+            e_steps = min(steps, 3)
+
+            def e2e_step():
+                if world == 1:
+                    return ctx.solve(A, b, n, 0)
+                sysm.load_host(A, b)
+                sysm.eliminate()
+                return sysm.result(0)
+
+            e2e_step()  # warm-up (allocations, pinned mappings)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                r = e2e_step()
+            barrier()
+            dt = time.perf_counter() - t0
+            assert r.status == 0 and np.array_equal(r.origin, res.origin)
+            h2d = int(A.nbytes + ((r1 - r0 + 63) // 64) * 8)
+            h2d = _dist.all_sum(h2d)
+            e2e = {"value": e_steps * work(n) / dt, "unit": UNIT, "steps": e_steps, "ms_per_step": 1e3 * dt / e_steps,
+                   "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": int(world * (res.origin.nbytes + 2 * 8 * ((n + 63) // 64) + 16)),
+                   "api": ("gf2b200_solve(ctx, A_host_pinned, b_host, m, n, stride64, mode=0, &result)" if world == 1 else
+                           "per rank: gf2b200_system_load_host(local rows, pinned) + system_eliminate + system_result")}
+            del tA, tb
+        except (RuntimeError, MemoryError) as exc:  # e.g. not enough pinnable host memory
+            e2e = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
 
     # ---- CPU baseline (rank 0, N = 1): the oracle's port on a bounded sample
     cpu = None
@@ -327,6 +311,15 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "residual_bad_rows": bad,
         }
+        ref1 = ROOT / "profiles" / "single_gpu_524288.json"
+        if world > 1 and n == 524288 and ref1.exists():
+            try:
+                one = json.loads(ref1.read_text())
+                line["speedup_vs_1gpu_same_n"] = {"value": one["ms_per_step"] / (tot_ms / steps),
+                                                  "one_gpu_ms_per_step": one["ms_per_step"],
+                                                  "source": "profiles/single_gpu_524288.json (committed 1-GPU run of the same n)"}
+            except Exception:
+                pass
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

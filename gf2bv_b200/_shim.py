@@ -25,7 +25,7 @@ EXPORTS = [
     "gf2b200_system_destroy", "gf2b200_system_local_rows", "gf2b200_system_load_host",
     "gf2b200_system_load_device", "gf2b200_system_generate", "gf2b200_system_eliminate",
     "gf2b200_system_result", "gf2b200_system_stats", "gf2b200_system_check_synthetic",
-    "gf2b200_host_alloc", "gf2b200_host_free", "gf2b200_create_shards",
+    "gf2b200_host_alloc", "gf2b200_host_free", "gf2b200_create_shards", "gf2b200_synth_host",
 ]
 
 
@@ -90,6 +90,7 @@ def lib() -> ctypes.CDLL:
     L.gf2b200_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.gf2b200_host_free.argtypes = [vp]
     L.gf2b200_host_free.restype = None
+    L.gf2b200_synth_host.argtypes = [u64p, u64p, i64, i64, i64, ctypes.c_uint64]
     L.gf2b200_destroy.argtypes = [vp]
     L.gf2b200_destroy.restype = None
     L.gf2b200_last_error.argtypes = [vp]
@@ -272,6 +273,16 @@ class System:
             self.close()
         except Exception:
             pass
+
+
+def synth_host(A: np.ndarray, b: np.ndarray, row0: int, n: int, seed: int = 1):
+    """Fill A (uint64[nrows, ceil(n/64)]) and b (packed bits) with rows row0.. of the
+    synthetic system (host memory; the e2e measurement's input)."""
+    assert A.dtype == np.uint64 and A.flags.c_contiguous and A.shape[1] == (n + 63) // 64
+    assert b.dtype == np.uint64 and b.size >= (A.shape[0] + 63) // 64
+    rc = lib().gf2b200_synth_host(A.ctypes.data, b.ctypes.data, row0, A.shape[0], n, seed)
+    if rc:
+        raise Gf2b200Error(f"gf2b200_synth_host failed ({rc})")
 
 
 _default_ctx: Optional[Context] = None

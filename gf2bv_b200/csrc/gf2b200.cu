@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "../../include/gf2b200.h"
@@ -50,6 +51,7 @@ struct gf2b200_ctx {
 	int rank, world; /* shard index of the first local shard, number of shards */
 	int n_local;     /* local shards: 1 (single, nccl) or world (loopback) */
 	ncclComm_t nccl; /* nccl contexts */
+	struct gf2b200_system *cached; /* device buffers of the last gf2b200_solve, reused for equal shapes */
 	char err[512];
 };
 
@@ -233,6 +235,7 @@ extern "C" int gf2b200_create_dist(gf2b200_ctx **out, int device, int rank, int 
 extern "C" void gf2b200_destroy(gf2b200_ctx *ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
+	if (ctx->cached) gf2b200_system_destroy(ctx->cached);
 	if (ctx->nccl) g_nccl.CommDestroy(ctx->nccl);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
 	free(ctx);
@@ -314,7 +317,7 @@ static cudaError_t shard_alloc(Shard &s, int world) {
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_pc[0], (size_t)M.mp * 8);
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_pc[1], (size_t)M.mp * 8);
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_state, sizeof(SolverState));
-	if (e == cudaSuccess) e = cudaMalloc(&s.d_pd, sizeof(PanelDesc));
+	if (e == cudaSuccess) e = cudaMalloc(&s.d_pd, 2 * sizeof(PanelDesc));
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_hist_r, (size_t)M.nw * 8);
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_hist_pm, (size_t)M.nw * 8);
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_ebuf, (size_t)M.ns * 4096);
@@ -533,17 +536,21 @@ static int forward_single(gf2b200_system *sys, long long *launches) {
 	k_extract_pc<<<grid_for(M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(M, 0, h.d_pc[0], 0);
 	(*launches)++;
 	const int apply_cap = ctx->n_sm * 4;
+	const bool fused = !getenv("GF2B200_NO_FUSED_SELECT"); /* diagnostic switch */
 	for (int w = 0; w < nw; w++) {
 		u64 colmask = ~0ULL;
 		if (w == nw - 1 && (M.n & 63)) colmask = (1ULL << (M.n & 63)) - 1;
 		u64 *pc_cur = h.d_pc[w & 1], *pc_next = h.d_pc[(w + 1) & 1];
-		k_select<<<1, SEL_THREADS, 0, st>>>(M, pc_cur, w, colmask, h.d_state, h.d_pd, h.d_hist_r,
-		                                    h.d_hist_pm);
+		/* two descriptions: the sweep of panel w writes panel w+1's while reading its own */
+		PanelDesc *pd = h.d_pd + (w & 1), *pdn = (w + 1 < nw && fused) ? h.d_pd + ((w + 1) & 1) : nullptr;
+		u64 colmask_next = ~0ULL;
+		if (w + 1 == nw - 1 && (M.n & 63)) colmask_next = (1ULL << (M.n & 63)) - 1;
+		k_select<<<1, SEL_THREADS, 0, st>>>(M, pc_cur, w, colmask, h.d_state, pd, h.d_hist_r, h.d_hist_pm);
 		int s0a = w >> 3;
-		k_apply<<<std::min(M.ns - s0a, apply_cap), 256, 0, st>>>(M, h.d_pd, h.d_ebuf, s0a);
+		k_apply<<<std::min(M.ns - s0a, apply_cap), 256, 0, st>>>(M, pd, h.d_ebuf, s0a);
 		if (prof) CK(ctx, cudaEventRecord(sys->ev[4 + 2 * w], st));
-		k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(M, h.d_pd, pc_cur, pc_next, h.d_ebuf, w,
-		                                                     (w + 1) >> 3);
+		k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(M, pd, pc_cur, pc_next, h.d_ebuf, w, (w + 1) >> 3,
+		                                                     pdn, h.d_state, h.d_hist_r, h.d_hist_pm, colmask_next);
 		if (prof) CK(ctx, cudaEventRecord(sys->ev[5 + 2 * w], st));
 		*launches += 3;
 	}
@@ -587,7 +594,8 @@ static int forward_sharded(gf2b200_system *sys, long long *launches, double *xby
 			const bool ev = prof && li == 0;
 			if (ev) CK(ctx, cudaEventRecord(sys->ev[4 + 2 * w], st));
 			k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(h.M, h.d_pd, h.d_pc[w & 1],
-			                                                     h.d_pc[(w + 1) & 1], h.d_ebuf, w, (w + 1) >> 3);
+			                                                     h.d_pc[(w + 1) & 1], h.d_ebuf, w, (w + 1) >> 3,
+			                                                     nullptr, nullptr, nullptr, nullptr, 0);
 			if (ev) CK(ctx, cudaEventRecord(sys->ev[5 + 2 * w], st));
 			li++;
 		}
@@ -646,7 +654,10 @@ extern "C" int gf2b200_system_eliminate(gf2b200_system *sys) {
 	double xbytes = 0;
 
 	CK(ctx, cudaEventRecord(ev_begin, st));
-	for (Shard &h : sys->sh) CK(ctx, cudaMemsetAsync(h.d_state, 0, sizeof(SolverState), st));
+	for (Shard &h : sys->sh) {
+		CK(ctx, cudaMemsetAsync(h.d_state, 0, sizeof(SolverState), st));
+		CK(ctx, cudaMemsetAsync(h.d_pd, 0, 2 * sizeof(PanelDesc), st));
+	}
 	int rc = sharded ? forward_sharded(sys, &launches, &xbytes) : forward_single(sys, &launches);
 	if (rc) return rc;
 	CK(ctx, cudaEventRecord(ev_fwd, st));
@@ -857,6 +868,47 @@ extern "C" int gf2b200_system_check_synthetic(gf2b200_system *sys, uint64_t seed
 	return GF2B200_OK;
 }
 
+/* Rows [row0, row0 + nrows) of the dense synthetic system written to
+ * HOST memory, row-major, for callers that measure the host-buffer path (bench e2e).
+ * A workload generator, not a solver: word(i, w) = mix(seed + PHI*(i*nw + w + 1)),
+ * b_i = <A_i, x*>; b is packed relative to row0. */
+extern "C" int gf2b200_synth_host(uint64_t *A, uint64_t *b, int64_t row0, int64_t nrows, int64_t n,
+                                  uint64_t seed) {
+	if (!A || !b || nrows < 0 || n < 1) return fail(nullptr, GF2B200_EINVAL, "bad argument");
+	const int64_t nw = (n + 63) / 64;
+	std::vector<u64> x((size_t)nw);
+	for (int64_t w = 0; w < nw; w++) x[w] = mix64((seed ^ 0xB200ULL) + GF2_PHI * (u64)(w + 1));
+	const u64 tail = (n & 63) ? ((1ULL << (n & 63)) - 1) : ~0ULL;
+	x[nw - 1] &= tail;
+	const int64_t blocks = (nrows + 63) / 64; /* 64 rows = one word of b: no sharing between threads */
+	unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 64));
+	nt = (unsigned)std::min<int64_t>(nt, std::max<int64_t>(blocks, 1));
+	auto work = [&](unsigned t) {
+		for (int64_t blk = t; blk < blocks; blk += nt) {
+			u64 bw = 0;
+			const int64_t i1 = std::min<int64_t>(nrows, (blk + 1) * 64);
+			for (int64_t il = blk * 64; il < i1; il++) {
+				uint64_t *row = A + il * nw;
+				const u64 base = (u64)((row0 + il) * nw);
+				u64 acc = 0;
+				for (int64_t w = 0; w < nw; w++) {
+					u64 v = mix64(seed + GF2_PHI * (base + (u64)w + 1));
+					if (w == nw - 1) v &= tail;
+					row[w] = v;
+					acc ^= v & x[w];
+				}
+				bw |= (u64)(__builtin_popcountll(acc) & 1) << (il & 63);
+			}
+			b[blk] = (uint64_t)bw;
+		}
+	};
+	std::vector<std::thread> th;
+	for (unsigned t = 1; t < nt; t++) th.emplace_back(work, t);
+	work(0);
+	for (auto &t : th) t.join();
+	return GF2B200_OK;
+}
+
 /* ---- one-shot host-buffer solve (what m4ri_solve's body becomes) ---------- */
 extern "C" int gf2b200_solve(gf2b200_ctx *ctx, const uint64_t *A, const uint64_t *b, int64_t m,
                              int64_t n, int64_t stride64, int mode, gf2b200_result *out) {
@@ -864,13 +916,25 @@ extern "C" int gf2b200_solve(gf2b200_ctx *ctx, const uint64_t *A, const uint64_t
 	memset(out, 0, sizeof *out);
 	if (mode != 0 && mode != 1) return fail(ctx, GF2B200_EINVAL, "Invalid mode");
 	if (ctx->nccl) return fail(ctx, GF2B200_EINVAL, "gf2b200_solve needs a single-process context");
-	gf2b200_system *sys = nullptr;
-	int rc = gf2b200_system_create(ctx, m, n, &sys);
+	/* repeated solves of one shape (the common case behind LinearSystem) keep their
+	 * HBM buffers: cudaMalloc/cudaFree of the matrix costs as much as its H2D copy */
+	gf2b200_system *sys = ctx->cached;
+	ctx->cached = nullptr;
+	int rc = GF2B200_OK;
+	if (sys && (sys->m_global != m || sys->n != n)) {
+		gf2b200_system_destroy(sys);
+		sys = nullptr;
+	}
+	if (!sys) rc = gf2b200_system_create(ctx, m, n, &sys);
 	if (rc) return rc;
 	rc = gf2b200_system_load_host(sys, A, b, stride64);
 	if (!rc) rc = gf2b200_system_eliminate(sys);
 	if (!rc) rc = gf2b200_system_result(sys, mode, out);
-	gf2b200_system_destroy(sys);
-	if (rc) out->status = rc;
+	if (rc) {
+		gf2b200_system_destroy(sys);
+		out->status = rc;
+	} else {
+		ctx->cached = sys;
+	}
 	return rc;
 }

@@ -85,25 +85,30 @@ k_elect(const u64 *__restrict__ cand_all, int G, int me, int w, u64 colmask, Sol
 	__shared__ int topsel[64], mv_src[64], mv_dst[64];
 	const int lane = threadIdx.x;
 	for (int c = lane; c < 64; c += 32) {
-		B[c] = 0;
-		TB[c] = 0;
 		sel[c] = -1;
 		topsel[c] = 0;
 	}
 	__syncwarp();
-	u64 pm = 0;
-	int nsel = 0;
-	for (int jj = 0; jj < G && pm != colmask; jj++) {
+	WarpBasis W;
+	W.B0 = W.B1 = W.T0 = W.T1 = 0;
+	W.pm = 0;
+	W.nsel = 0;
+	for (int jj = 0; jj < G && W.pm != colmask; jj++) {
 		const int src = (w + jj) % G;
 		const u64 *cb = cand_all + (long long)src * CAND_W;
 		const int cnt = (int)cb[0];
-		for (int q0 = 0; q0 < cnt && pm != colmask; q0 += 32) {
-			const int q = q0 + lane;
-			const u64 v = (q < cnt) ? cb[1 + q] : 0;
-			warp0_insert(B, TB, sel, pm, nsel, colmask, v, 0, src * 64 + q, lane);
+		/* lanes fetch 32 candidates at a time; each is then broadcast and inserted */
+		for (int q0 = 0; q0 < cnt && W.pm != colmask; q0 += 32) {
+			const u64 mine = (q0 + lane < cnt) ? cb[1 + q0 + lane] : 0;
+			const int nq = min(32, cnt - q0);
+			for (int j = 0; j < nq && W.pm != colmask; j++)
+				wb_insert(W, sel, shfl64(mine, j), 0, src * 64 + q0 + j, lane);
 		}
 	}
+	wb_store(W, B, TB, lane);
 	__syncwarp();
+	const u64 pm = W.pm;
+	const int nsel = W.nsel;
 	const int k = nsel;
 	const long long r_loc = st->r_loc;
 	for (int c = lane; c < 64; c += 32) {

@@ -54,6 +54,8 @@ struct PanelDesc {
 	long long r1;    /* first active (not yet pivot) row after this panel */
 	int k;           /* pivots found in this panel */
 	int nmove;       /* displaced rows to relocate */
+	int valid;       /* panel index + 1 this description belongs to (0: none) */
+	int pad;
 	u64 pm;          /* pivot column mask within the panel word */
 	u64 TB[64];      /* by column c: combination of selected rows giving E_c; 0 if c is free */
 	int sel[64];     /* physical row of the l-th selected row */
@@ -184,55 +186,58 @@ __global__ void k_extract_pc(Mat M, int w, u64 *__restrict__ pc, long long row0)
  * valid column of the panel is a pivot.
  *
  * All 32 warps reduce 1024 rows against the basis snapshot and compact the
- * survivors; warp 0 then inserts them one at a time: __ballot_sync finds the
- * next candidate lane, __shfl_sync broadcasts its pivot word.
+ * survivors (warp ballot); warp 0 then inserts them one at a time into a
+ * register-resident basis (WarpBasis: warp-wide REDUX.XOR reduction).
  * ---------------------------------------------------------------------- */
 #define SEL_THREADS 1024
 
-__device__ __forceinline__ void warp0_insert(u64 *B, u64 *TB, int *sel, u64 &pm, int &nsel,
-                                             const u64 colmask, u64 v, u64 tv, int row, int lane) {
-	/* re-reduce against pivots added since the snapshot (B is RREF: one shot) */
-	u64 x = v & pm;
-	while (x) {
-		int c = __ffsll((long long)x) - 1;
-		x &= x - 1;
-		v ^= B[c];
-		tv ^= TB[c];
+/* XOR basis of <= 64 panel words held in the registers of ONE warp: lane L keeps
+ * the basis vectors keyed by columns L and L+32 (0 while the column is not a
+ * pivot) and, beside each, the set of selected rows that were XORed to form it.
+ * The basis is kept in RREF, so a candidate is reduced against ALL of it at once:
+ * every lane offers its vectors where the candidate has the key bit, and two
+ * warp-wide REDUX.XOR pairs fold the offers -- no serial walk over set bits. */
+struct WarpBasis {
+	u64 B0, B1, T0, T1;
+	u64 pm;   /* pivot columns so far (uniform) */
+	int nsel; /* selected rows so far (uniform) */
+};
+
+__device__ __forceinline__ u64 warp_xor64(u64 v) {
+	unsigned lo = __reduce_xor_sync(0xffffffffu, (unsigned)v);
+	unsigned hi = __reduce_xor_sync(0xffffffffu, (unsigned)(v >> 32));
+	return ((u64)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void wb_load(WarpBasis &W, const u64 *B, const u64 *TB, u64 pm, int nsel, int lane) {
+	W.B0 = B[lane]; W.B1 = B[lane + 32];
+	W.T0 = TB[lane]; W.T1 = TB[lane + 32];
+	W.pm = pm; W.nsel = nsel;
+}
+
+__device__ __forceinline__ void wb_store(const WarpBasis &W, u64 *B, u64 *TB, int lane) {
+	B[lane] = W.B0; B[lane + 32] = W.B1;
+	TB[lane] = W.T0; TB[lane + 32] = W.T1;
+}
+
+/* v, tv, row uniform across the warp.  Returns true if v raised the rank. */
+__device__ __forceinline__ bool wb_insert(WarpBasis &W, int *sel, u64 v, u64 tv, int row, int lane) {
+	const u64 m0 = 0ULL - ((v >> lane) & 1), m1 = 0ULL - ((v >> (lane + 32)) & 1);
+	v ^= warp_xor64((W.B0 & m0) ^ (W.B1 & m1));
+	if (!v) return false;
+	tv ^= warp_xor64((W.T0 & m0) ^ (W.T1 & m1));
+	const int c = __ffsll((long long)v) - 1;
+	tv ^= 1ULL << W.nsel;
+	if ((W.B0 >> c) & 1) { W.B0 ^= v; W.T0 ^= tv; }
+	if ((W.B1 >> c) & 1) { W.B1 ^= v; W.T1 ^= tv; }
+	if (lane == (c & 31)) {
+		if (c < 32) { W.B0 = v; W.T0 = tv; }
+		else { W.B1 = v; W.T1 = tv; }
 	}
-	__syncwarp();
-	while (pm != colmask) {
-		unsigned bal = __ballot_sync(0xffffffffu, v != 0);
-		if (!bal) break;
-		int src = __ffs((int)bal) - 1;
-		u64 u = shfl64(v, src);
-		u64 tu = shfl64(tv, src);
-		int urow = __shfl_sync(0xffffffffu, row, src);
-		int c = __ffsll((long long)u) - 1;
-		tu ^= 1ULL << nsel;
-#pragma unroll
-		for (int h = 0; h < 2; h++) {
-			int cc = lane + 32 * h;
-			if ((pm >> cc) & 1) {
-				u64 b = B[cc];
-				if ((b >> c) & 1) {
-					B[cc] = b ^ u;
-					TB[cc] ^= tu;
-				}
-			}
-		}
-		if (lane == 0) {
-			B[c] = u;
-			TB[c] = tu;
-			sel[nsel] = urow;
-		}
-		pm |= 1ULL << c;
-		nsel++;
-		if ((v >> c) & 1) {
-			v ^= u;
-			tv ^= tu;
-		}
-		__syncwarp();
-	}
+	if (lane == 0) sel[W.nsel] = row;
+	W.pm |= 1ULL << c;
+	W.nsel++;
+	return true;
 }
 
 /* Shared scan body: absorbs rows [r, m) of pc into the basis.  Returns via smem. */
@@ -282,29 +287,23 @@ __device__ __forceinline__ void select_scan(SelectSmem &S, const u64 *__restrict
 		}
 		__syncthreads();
 		if (warp == 0) {
-			int nsel = S.nsel;
-			for (int q0 = 0; q0 < total && pm != colmask; q0 += 32) {
-				int q = q0 + lane;
-				u64 cv = (q < total) ? S.qv[q] : 0;
-				u64 ctv = (q < total) ? S.qtv[q] : 0;
-				int crow = (q < total) ? S.qrow[q] : -1;
-				warp0_insert(S.B, S.TB, S.sel, pm, nsel, colmask, cv, ctv, crow, lane);
-			}
+			/* survivors, one at a time, against the register-resident basis */
+			WarpBasis W;
+			wb_load(W, S.B, S.TB, pm, S.nsel, lane);
+			for (int q = 0; q < total && W.pm != colmask; q++)
+				wb_insert(W, S.sel, S.qv[q], S.qtv[q], S.qrow[q], lane);
+			wb_store(W, S.B, S.TB, lane);
 			if (lane == 0) {
-				S.pm = pm;
-				S.nsel = nsel;
+				S.pm = W.pm;
+				S.nsel = W.nsel;
 			}
 		}
 		__syncthreads();
 	}
 }
 
-__global__ void __launch_bounds__(SEL_THREADS, 1)
-k_select(Mat M, u64 *__restrict__ pc, int w, u64 colmask, SolverState *st, PanelDesc *pd,
-         long long *hist_r, u64 *hist_pm) {
-	__shared__ SelectSmem S;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const long long r = st->r, m = M.m;
+__device__ __forceinline__ void select_init(SelectSmem &S) {
+	const int tid = threadIdx.x;
 	if (tid < 64) {
 		S.B[tid] = 0;
 		S.TB[tid] = 0;
@@ -315,18 +314,21 @@ k_select(Mat M, u64 *__restrict__ pc, int w, u64 colmask, SolverState *st, Panel
 		S.pm = 0;
 		S.nsel = 0;
 	}
-	__syncthreads();
-	select_scan(S, pc, r, m, colmask);
-	if (warp != 0) return;
-	/* ---- finalise (warp 0) ---- */
+}
+
+/* Warp 0: turn the finished scan into the panel description.  Rows r..r+k-1
+ * become the echelon rows; selected rows already there stay, the others
+ * ("displaced") move to the positions vacated by selected rows. */
+__device__ __forceinline__ void select_finalize(SelectSmem &S, u64 *__restrict__ pc, int w, long long r,
+                                                SolverState *st, PanelDesc *pd, long long *hist_r,
+                                                u64 *hist_pm) {
+	const int lane = threadIdx.x & 31;
 	const u64 pm = S.pm;
 	const int k = S.nsel;
 	for (int c = lane; c < 64; c += 32) {
 		pd->TB[c] = ((pm >> c) & 1) ? S.TB[c] : 0;
 		pd->sel[c] = S.sel[c];
 	}
-	/* rows r..r+k-1 become the echelon rows; selected rows already there stay,
-	 * the others ("displaced") move to the positions vacated by selected rows */
 	for (int l = lane; l < k; l += 32) {
 		int srow = S.sel[l];
 		if (srow < r + k) S.topsel[srow - (int)r] = 1;
@@ -366,11 +368,28 @@ k_select(Mat M, u64 *__restrict__ pc, int w, u64 colmask, SolverState *st, Panel
 		pd->k = k;
 		pd->nmove = ndis;
 		pd->pm = pm;
+		pd->valid = w + 1;
 		st->r = r + k;
 		st->r_loc = r + k;
 		hist_r[w] = r;
 		hist_pm[w] = pm;
 	}
+}
+
+/* Pivot search of panel w.  Usually a no-op: the sweep of panel w-1 already ran
+ * the search on the first 1024 active rows (see k_sweep) and, when that found a
+ * full set of pivots, marked the description valid.  Otherwise scan everything. */
+__global__ void __launch_bounds__(SEL_THREADS, 1)
+k_select(Mat M, u64 *__restrict__ pc, int w, u64 colmask, SolverState *st, PanelDesc *pd,
+         long long *hist_r, u64 *hist_pm) {
+	__shared__ SelectSmem S;
+	if (pd->valid == w + 1) return;
+	const long long r = st->r, m = M.m;
+	select_init(S);
+	__syncthreads();
+	select_scan(S, pc, r, m, colmask);
+	if (threadIdx.x >= 32) return;
+	select_finalize(S, pc, w, r, st, pd, hist_r, hist_pm);
 }
 
 /* ------------------------------------------------------------------------
@@ -452,7 +471,11 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
 #define SWEEP_RU (SWEEP_THREADS / 4 * SWEEP_U) /* rows per unit */
 #define SWEEP_LINES (8 * 128 + 256)
 #define SWEEP_PARTS (8 * 24 + 32)
-#define SWEEP_SMEM (SWEEP_LINES * 128 + SWEEP_PARTS * 64 + 64 * 64 + 16)
+/* 160 KiB of tables + the mbarrier.  The build scratch (E tile, partial tables) and
+ * the fused pivot search's scratch alias table space, so the whole CTA stays under
+ * the 164 KiB shared-memory carve-out and the SM keeps 92 KiB of L1 for the
+ * streaming loads in flight (a 182 KiB layout measured 20% slower at 228 KiB carve-out). */
+#define SWEEP_SMEM (SWEEP_LINES * 128 + 16)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) {
 	return (unsigned)__cvta_generic_to_shared(p);
@@ -487,8 +510,10 @@ __device__ __forceinline__ void xor4(uint4 &a, const uint4 &b) {
 	a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w;
 }
 
-/* Builds TD from the pivot-row tile E (64 columns x 64 B).  All SWEEP_THREADS
- * threads; two __syncthreads inside, one more needed by the caller before use. */
+/* Builds TD from the pivot-row tile E (64 columns x 64 B).  E and the partial
+ * tables P live inside the area of field 8 (the last 32 KiB of TD), which is
+ * therefore written last, from registers.  All SWEEP_THREADS threads; ends with a
+ * __syncthreads. */
 __device__ __forceinline__ void sweep_build_tables(uint4 *TD, uint4 *P, const uint4 *E, int tid) {
 	/* partial tables: field g < 8 (columns 7g..7g+6): 8 entries over its low 3
 	 * columns, 16 over its high 4; field 8 (columns 56..63): 16 + 16 */
@@ -511,32 +536,44 @@ __device__ __forceinline__ void sweep_build_tables(uint4 *TD, uint4 *P, const ui
 		P[tid] = acc;
 	}
 	__syncthreads();
-	/* full tables, both halves of each line: item = (line, half, chunk) */
-	for (int it = tid; it < SWEEP_LINES * 8; it += SWEEP_THREADS) {
+	/* fields 0..7, both halves of each line: item = (line, half, chunk) */
+	for (int it = tid; it < 1024 * 8; it += SWEEP_THREADS) {
 		const int L = it >> 3, ch = it & 3;
-		uint4 a, b;
-		if (L < 1024) {
-			const int g = L >> 7, e = L & 127;
-			a = P[(g * 24 + (e & 7)) * 4 + ch];
-			b = P[(g * 24 + 8 + (e >> 3)) * 4 + ch];
-		} else {
-			const int e = L - 1024;
-			a = P[(192 + (e & 15)) * 4 + ch];
-			b = P[(208 + (e >> 4)) * 4 + ch];
-		}
-		xor4(a, b);
+		const int g = L >> 7, e = L & 127;
+		uint4 a = P[(g * 24 + (e & 7)) * 4 + ch];
+		xor4(a, P[(g * 24 + 8 + (e >> 3)) * 4 + ch]);
 		TD[it] = a;
 	}
+	/* field 8 overwrites the scratch: values to registers, barrier, then store */
+	uint4 f8[2];
+#pragma unroll
+	for (int q = 0; q < 2; q++) {
+		const int it = tid + q * SWEEP_THREADS; /* 256 lines x 8 */
+		const int e = it >> 3, ch = it & 3;
+		f8[q] = P[(192 + (e & 15)) * 4 + ch];
+		xor4(f8[q], P[(208 + (e >> 4)) * 4 + ch]);
+	}
+	__syncthreads();
+#pragma unroll
+	for (int q = 0; q < 2; q++) TD[1024 * 8 + tid + q * SWEEP_THREADS] = f8[q];
+	__syncthreads();
 }
+
+static_assert(sizeof(SelectSmem) <= 1024 * 128, "pivot-search scratch must fit inside the tables of fields 0..7");
+static_assert((64 * 4 + SWEEP_PARTS * 4) * 16 <= 256 * 128, "build scratch must fit inside field 8's lines");
+#define SWEEP_SEL_PAD 4 /* units CTA 0 is spared to make room for the fused pivot search */
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
 k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
-        u64 *__restrict__ pc_next, const uint4 *__restrict__ ebuf, int w, int s0) {
+        u64 *__restrict__ pc_next, const uint4 *__restrict__ ebuf, int w, int s0,
+        PanelDesc *pd_next, SolverState *st, long long *hist_r, u64 *hist_pm, u64 colmask_next) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint4 *TD = reinterpret_cast<uint4 *>(smem_raw);
-	uint4 *P = TD + SWEEP_LINES * 8;
-	uint4 *E = P + SWEEP_PARTS * 4;
-	u64 *bar = reinterpret_cast<u64 *>(E + 64 * 4);
+	uint4 *E = TD + 1024 * 8;      /* build scratch inside field 8's lines */
+	uint4 *P = E + 64 * 4;
+	u64 *bar = reinterpret_cast<u64 *>(TD + SWEEP_LINES * 8);
+	/* scratch of the fused pivot search of panel w+1 (pd_next != nullptr): over the tables */
+	SelectSmem &S = *reinterpret_cast<SelectSmem *>(smem_raw);
 
 	const int tid = threadIdx.x;
 	const int k = pd->k;
@@ -556,8 +593,12 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 	const long long rows = m - r1;
 	const long long nchunks = (rows + SWEEP_RU - 1) / SWEEP_RU;
 	const long long units = (long long)(M.ns - s0) * nchunks;
-	const long long u0 = units * blockIdx.x / gridDim.x;
-	const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
+	/* unit 0 = (strip of word w+1, first 1024 active rows) carries the fused pivot
+	 * search: its CTA gets SWEEP_SEL_PAD fewer units */
+	const long long vpad = pd_next ? max(0LL, min((long long)SWEEP_SEL_PAD, units / gridDim.x - 1)) : 0;
+	const long long vunits = units + vpad;
+	const long long u0 = max(0LL, vunits * blockIdx.x / gridDim.x - vpad);
+	const long long u1 = vunits * (blockIdx.x + 1) / gridDim.x - vpad;
 	if (u0 >= u1) return;
 	if (tid == 0) {
 		mbar_init(bar, 1);
@@ -584,7 +625,6 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 			mbar_wait(bar, phase);
 			phase ^= 1;
 			sweep_build_tables(TD, P, E, tid);
-			__syncthreads();
 			cur = s;
 		}
 		const long long row0 = r1 + chunk * SWEEP_RU + rl;
@@ -627,6 +667,27 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 				long long row = row0 + (SWEEP_THREADS / 4) * q;
 				pc_next[row] = (wn & 1) ? (((u64)v.w << 32) | v.z) : (((u64)v.y << 32) | v.x);
 			}
+		}
+		if (pd_next && u == 0) {
+			/* This CTA just produced panel word w+1 of the first 1024 active rows.
+			 * Search them for the next panel's pivots while the other SMs keep
+			 * sweeping; a full set (the usual case on dense systems) or an exhausted
+			 * row range makes the description final and turns k_select into a no-op.
+			 * The rows' other strips are complete by the time k_apply runs. */
+			__threadfence();
+			__syncthreads(); /* also: every lookup of this unit is done, the tables may be clobbered */
+			cur = -1;        /* ... and are rebuilt before the next unit */
+			select_init(S);
+			__syncthreads();
+			const long long lim = min(m, r1 + (long long)SWEEP_RU);
+			select_scan(S, pc_next, r1, lim, colmask_next);
+			if (tid < 32) {
+				if (S.pm == colmask_next || lim == m)
+					select_finalize(S, pc_next, wn, r1, st, pd_next, hist_r, hist_pm);
+				else if (tid == 0)
+					pd_next->valid = 0;
+			}
+			__syncthreads();
 		}
 	}
 }

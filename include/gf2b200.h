@@ -139,6 +139,11 @@ int gf2b200_system_stats(const gf2b200_system *sys, gf2b200_stats *out);
  * A_i x != b_i, summed over this rank's rows; x = ceil(n/64) host words. */
 int gf2b200_system_check_synthetic(gf2b200_system *sys, uint64_t seed, const uint64_t *x,
                                    int64_t *bad_rows);
+/* Rows [row0, row0+nrows) of the same synthetic system written row-major to HOST
+ * memory (A: nrows x ceil(n/64) words, b: nrows bits packed from bit 0): the input
+ * of the host-buffer (e2e) measurement.  A workload generator, not a solver. */
+int gf2b200_synth_host(uint64_t *A, uint64_t *b, int64_t row0, int64_t nrows, int64_t n,
+                       uint64_t seed);
 
 #ifdef __cplusplus
 }
