@@ -642,7 +642,7 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 		for (int q = 0; q < SWEEP_U; q++) {
 			long long row = row0 + (SWEEP_THREADS / 4) * q;
 			act[q] = (row < m) && (cf[q] != 0 || force);
-			if (act[q]) d[q] = p[(long long)(SWEEP_THREADS / 4) * q * 4];
+			if (act[q]) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / 4) * q * 4);
 		}
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {
@@ -662,7 +662,7 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 			xor4(v, TLOOK(7 * 16384 + ((hi >> 10) & 0x3F80u)));
 			xor4(v, TLOOK(8 * 16384 + ((hi >> 17) & 0x7F80u)));
 #undef TLOOK
-			p[(long long)(SWEEP_THREADS / 4) * q * 4] = v;
+			__stcg(p + (long long)(SWEEP_THREADS / 4) * q * 4, v);
 			if (force && ch == nch) {
 				long long row = row0 + (SWEEP_THREADS / 4) * q;
 				pc_next[row] = (wn & 1) ? (((u64)v.w << 32) | v.z) : (((u64)v.y << 32) | v.x);
