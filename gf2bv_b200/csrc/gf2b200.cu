@@ -68,9 +68,9 @@ struct Shard {
 	/* sharded systems only */
 	DistPanel *d_dp;
 	unsigned char *d_hist_owner;
-	u64 *d_cand_send, *d_cand_all;
-	int *d_selrow;
-	uint4 *d_rows_send, *d_rows_all;
+	XchBlock *xch;    /* behind the matrix, same allocation (one IPC handle maps both) */
+	PeerTable *d_pt;  /* peers' matrices / exchange blocks as mapped in this process */
+	std::vector<void *> ipc_opened;
 	/* back-substitution */
 	u64 *d_x;    /* nw + 1 words */
 	u64 *d_slab; /* BS_S*64 rows x BS_W */
@@ -87,6 +87,7 @@ struct gf2b200_system {
 	long long rank;
 	int inconsistent;
 	int eliminated;
+	unsigned epoch_base; /* flag epochs of the peer-memory exchange only ever grow */
 	gf2b200_stats stats;
 	std::vector<cudaEvent_t> ev;
 };
@@ -291,13 +292,11 @@ static void shard_free(Shard &s) {
 	cudaFree(s.d_hist_r);
 	cudaFree(s.d_hist_pm);
 	cudaFree(s.d_ebuf);
+	for (void *p : s.ipc_opened) cudaIpcCloseMemHandle(p);
+	s.ipc_opened.clear();
 	cudaFree(s.d_dp);
 	cudaFree(s.d_hist_owner);
-	cudaFree(s.d_cand_send);
-	cudaFree(s.d_cand_all);
-	cudaFree(s.d_selrow);
-	cudaFree(s.d_rows_send);
-	cudaFree(s.d_rows_all);
+	cudaFree(s.d_pt);
 	cudaFree(s.d_x);
 	if (s.d_slab_all != s.d_slab) cudaFree(s.d_slab_all);
 	cudaFree(s.d_slab);
@@ -313,7 +312,9 @@ extern "C" void gf2b200_system_destroy(gf2b200_system *sys) {
 
 static cudaError_t shard_alloc(Shard &s, int world) {
 	const Mat &M = s.M;
-	cudaError_t e = cudaMalloc(&s.M.base, (size_t)M.ns * (size_t)M.mp * 64);
+	/* matrix + (sharded) exchange block in ONE allocation */
+	const size_t mat_bytes = (size_t)M.ns * (size_t)M.mp * 64;
+	cudaError_t e = cudaMalloc(&s.M.base, mat_bytes + (world > 1 ? sizeof(XchBlock) : 0));
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_pc[0], (size_t)M.mp * 8);
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_pc[1], (size_t)M.mp * 8);
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_state, sizeof(SolverState));
@@ -329,13 +330,73 @@ static cudaError_t shard_alloc(Shard &s, int world) {
 		if (e == cudaSuccess) e = cudaMalloc(&s.d_slab_all, (size_t)world * BS_S * 64 * BS_W * 8);
 		if (e == cudaSuccess) e = cudaMalloc(&s.d_dp, sizeof(DistPanel));
 		if (e == cudaSuccess) e = cudaMalloc(&s.d_hist_owner, (size_t)M.nw * 64);
-		if (e == cudaSuccess) e = cudaMalloc(&s.d_cand_send, CAND_W * 8);
-		if (e == cudaSuccess) e = cudaMalloc(&s.d_cand_all, (size_t)world * CAND_W * 8);
-		if (e == cudaSuccess) e = cudaMalloc(&s.d_selrow, 64 * sizeof(int));
-		if (e == cudaSuccess) e = cudaMalloc(&s.d_rows_send, (size_t)64 * M.ns * 64);
-		if (e == cudaSuccess) e = cudaMalloc(&s.d_rows_all, (size_t)world * 64 * M.ns * 64);
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_pt, sizeof(PeerTable));
+		if (e == cudaSuccess) {
+			s.xch = reinterpret_cast<XchBlock *>(reinterpret_cast<char *>(s.M.base) + mat_bytes);
+			e = cudaMemset(s.xch, 0, sizeof(XchBlock));
+		}
 	}
 	return e;
+}
+
+/* Fill every local shard's PeerTable.  Loopback: the peers are the local shards.
+ * NCCL context: every rank exports its matrix allocation (matrix + exchange block)
+ * as a CUDA IPC handle, the handles travel by ncclAllGather, and each rank maps its
+ * peers' allocations -- after this the panel exchange is plain NVLink loads/stores
+ * issued by our own kernels. */
+static int map_peers(gf2b200_system *sys) {
+	gf2b200_ctx *ctx = sys->ctx;
+	const int G = ctx->world;
+	const long long m = sys->m_global;
+	PeerTable pt;
+	memset(&pt, 0, sizeof pt);
+	for (int g = 0; g < G; g++) {
+		long long rows = m * (g + 1) / G - m * g / G;
+		pt.mp[g] = (std::max<long long>(rows, 1) + 15) / 16 * 16;
+	}
+	if (!ctx->nccl) {
+		for (Shard &h : sys->sh) {
+			pt.base[h.index] = h.M.base;
+			pt.xch[h.index] = h.xch;
+		}
+		for (Shard &h : sys->sh)
+			CK(ctx, cudaMemcpy(h.d_pt, &pt, sizeof pt, cudaMemcpyHostToDevice));
+		return GF2B200_OK;
+	}
+	Shard &h = sys->sh[0];
+	const size_t mat_bytes = (size_t)h.M.ns * (size_t)h.M.mp * 64;
+	cudaIpcMemHandle_t mine;
+	CK(ctx, cudaIpcGetMemHandle(&mine, h.M.base));
+	std::vector<cudaIpcMemHandle_t> all((size_t)G);
+	char *d_h = nullptr;
+	CK(ctx, cudaMalloc(&d_h, sizeof(mine) * (size_t)(G + 1)));
+	cudaError_t e = cudaMemcpyAsync(d_h + sizeof(mine) * (size_t)G, &mine, sizeof mine, cudaMemcpyHostToDevice,
+	                                ctx->stream);
+	ncclResult_t r = g_nccl.AllGather(d_h + sizeof(mine) * (size_t)G, d_h, sizeof mine, ncclUint8, ctx->nccl,
+	                                  ctx->stream);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(all.data(), d_h, sizeof(mine) * (size_t)G, cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	cudaFree(d_h);
+	if (r != ncclSuccess) return fail(ctx, GF2B200_ENCCL, "ncclAllGather(ipc handles): %s", g_nccl.GetErrorString(r));
+	if (e != cudaSuccess) return fail(ctx, GF2B200_ECUDA, "ipc handle exchange: %s", cudaGetErrorString(e));
+	for (int g = 0; g < G; g++) {
+		void *p = h.M.base;
+		if (g != h.index) {
+			e = cudaIpcOpenMemHandle(&p, all[g], cudaIpcMemLazyEnablePeerAccess);
+			if (e != cudaSuccess) {
+				cudaGetLastError();
+				return fail(ctx, GF2B200_ECUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+			}
+			h.ipc_opened.push_back(p);
+		}
+		pt.base[g] = (u64 *)p;
+		/* the peer's exchange block sits behind ITS matrix: ns is global, mp is per shard */
+		pt.xch[g] = reinterpret_cast<XchBlock *>((char *)p + (size_t)h.M.ns * (size_t)pt.mp[g] * 64);
+	}
+	(void)mat_bytes;
+	CK(ctx, cudaMemcpy(h.d_pt, &pt, sizeof pt, cudaMemcpyHostToDevice));
+	return GF2B200_OK;
 }
 
 extern "C" int gf2b200_system_create(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2b200_system **out) {
@@ -370,8 +431,7 @@ extern "C" int gf2b200_system_create(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2
 		h.d_pc[0] = h.d_pc[1] = nullptr;
 		h.d_state = nullptr; h.d_pd = nullptr; h.d_hist_r = nullptr; h.d_hist_pm = nullptr;
 		h.d_ebuf = nullptr; h.d_dp = nullptr; h.d_hist_owner = nullptr;
-		h.d_cand_send = h.d_cand_all = nullptr; h.d_selrow = nullptr;
-		h.d_rows_send = h.d_rows_all = nullptr;
+		h.xch = nullptr; h.d_pt = nullptr;
 		h.d_x = h.d_slab = h.d_slab_all = nullptr;
 		e = shard_alloc(h, ctx->world);
 	}
@@ -381,6 +441,14 @@ extern "C" int gf2b200_system_create(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2
 		cudaGetLastError();
 		gf2b200_system_destroy(s);
 		return rc;
+	}
+	s->epoch_base = 0;
+	if (ctx->world > 1) {
+		int rc = map_peers(s);
+		if (rc) {
+			gf2b200_system_destroy(s);
+			return rc;
+		}
 	}
 	*out = s;
 	return GF2B200_OK;
@@ -559,12 +627,15 @@ static int forward_single(gf2b200_system *sys, long long *launches) {
 	return GF2B200_OK;
 }
 
-/* forward elimination of a row-sharded system (nccl or loopback) */
+/* forward elimination of a row-sharded system: the per-panel exchange goes through
+ * peer memory (gf2b200_dist.cuh); an NCCL context adds the flag waits, a loopback
+ * context gets the same ordering from the single stream */
 static int forward_sharded(gf2b200_system *sys, long long *launches, double *xbytes) {
 	gf2b200_ctx *ctx = sys->ctx;
 	cudaStream_t st = ctx->stream;
 	const bool prof = ctx->profile != 0;
 	const int G = ctx->world;
+	const int barriers = ctx->nccl ? 1 : 0;
 	const int nw = sys->sh[0].M.nw, ns = sys->sh[0].M.ns;
 	const int apply_cap = ctx->n_sm * 4;
 	for (Shard &h : sys->sh) {
@@ -575,22 +646,23 @@ static int forward_sharded(gf2b200_system *sys, long long *launches, double *xby
 		u64 colmask = ~0ULL;
 		if (w == nw - 1 && (sys->n & 63)) colmask = (1ULL << (sys->n & 63)) - 1;
 		const int s0a = w >> 3, nsr = ns - s0a;
+		const unsigned epoch = sys->epoch_base + (unsigned)w + 1;
 		for (Shard &h : sys->sh)
-			k_select_local<<<1, SEL_THREADS, 0, st>>>(h.M, h.d_pc[w & 1], colmask, h.d_state, h.d_cand_send,
-			                                          h.d_selrow);
-		int rc = all_gather(sys, &Shard::d_cand_send, &Shard::d_cand_all, CAND_W * 8, xbytes);
-		if (rc) return rc;
-		for (Shard &h : sys->sh) {
-			k_elect<<<1, 32, 0, st>>>(h.d_cand_all, G, h.index, w, colmask, h.d_state, h.d_pd, h.d_dp,
-			                          h.d_selrow, h.d_pc[w & 1], h.d_hist_r, h.d_hist_pm, h.d_hist_owner);
-			k_pack<<<std::min(nsr, apply_cap), 256, 0, st>>>(h.M, h.d_dp, h.d_rows_send, s0a);
-		}
-		rc = all_gather(sys, &Shard::d_rows_send, &Shard::d_rows_all, (size_t)64 * nsr * 64, xbytes);
-		if (rc) return rc;
+			k_select_publish<<<1, SEL_THREADS, 0, st>>>(h.M, h.d_pc[w & 1], colmask, h.d_state, h.d_pt, h.index, G,
+			                                            epoch, barriers);
+		for (Shard &h : sys->sh)
+			k_elect<<<1, 32, 0, st>>>(h.xch, G, h.index, w, colmask, h.d_state, h.d_pd, h.d_dp, h.d_pc[w & 1],
+			                          h.d_hist_r, h.d_hist_pm, h.d_hist_owner, epoch, barriers);
+		for (Shard &h : sys->sh)
+			k_apply_pull<<<std::min(nsr, apply_cap), 256, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_pt, h.d_ebuf, s0a);
+		if (barriers)
+			for (Shard &h : sys->sh) {
+				k_peer_barrier<<<1, 64, 0, st>>>(h.xch, h.d_pt, h.index, G, epoch, h.d_state);
+				(*launches)++;
+			}
 		int li = 0;
 		for (Shard &h : sys->sh) {
-			k_apply_dist<<<std::min(nsr, apply_cap), 256, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_rows_all, h.d_ebuf,
-			                                                      s0a);
+			k_apply_commit<<<std::min(nsr, apply_cap), 256, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_ebuf, s0a);
 			const bool ev = prof && li == 0;
 			if (ev) CK(ctx, cudaEventRecord(sys->ev[4 + 2 * w], st));
 			k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(h.M, h.d_pd, h.d_pc[w & 1],
@@ -600,7 +672,10 @@ static int forward_sharded(gf2b200_system *sys, long long *launches, double *xby
 			li++;
 		}
 		*launches += 5 * (long long)sys->sh.size();
+		/* per shard: candidate blocks stored to G peers + 64 pivot-row pieces pulled per strip */
+		*xbytes += (double)sys->sh.size() * ((double)G * CAND_W * 8 + 64.0 * nsr * 64.0);
 	}
+	sys->epoch_base += (unsigned)nw;
 	for (Shard &h : sys->sh) {
 		k_check<<<grid_for(h.M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(h.M, h.d_state);
 		(*launches)++;
@@ -683,7 +758,10 @@ extern "C" int gf2b200_system_eliminate(gf2b200_system *sys) {
 	CK(ctx, cudaStreamSynchronize(st));
 	sys->rank = hs[0].r;
 	int bad = 0;
-	for (const SolverState &s : hs) bad |= s.inconsistent;
+	for (const SolverState &s : hs) {
+		bad |= s.inconsistent;
+		if (s.fault) return fail(ctx, GF2B200_ECUDA, "peer-memory exchange timed out waiting for another rank");
+	}
 	if (ctx->nccl) {
 		/* a shard with an active row "0 = 1" makes the whole system inconsistent */
 		int *d_flag = nullptr;

@@ -4,23 +4,33 @@
  *
  * Sharding: shard g of G holds the contiguous global rows
  * [g*m/G, (g+1)*m/G) in its own strip-major Mat; columns are never split, so all
- * XOR traffic of the sweep stays in local HBM.  Per 64-column panel w:
+ * XOR traffic of the sweep stays in local HBM.  The per-panel exchange runs over
+ * PEER MEMORY (every rank maps every peer's matrix + exchange block through CUDA
+ * IPC; NVLink loads/stores issued by these kernels), not through collectives:
  *
- *   k_select_local  each shard reduces ITS active rows' panel words to <= 64
- *                   candidate rows (a basis of their span) and publishes the
- *                   candidates' raw 64-bit panel words;
- *   [exchange 1]    all-gather of the candidate words (G * 66 words);
- *   k_elect         every shard runs the same deterministic election over the
- *                   G*64 candidates (priority rotates with w so rows deplete
- *                   evenly): the elected rows' pivot columns are the panel's
- *                   GLOBAL column rank profile -- what _mzd_pluq reports in Q
- *                   (reference _internal.c:433) -- because the
- *                   union of the local bases spans the global active row space;
- *   k_pack          owners copy their elected rows (trailing strips) to a send slab;
- *   [exchange 2]    all-gather of the slabs: the "broadcast of each pivot row";
- *   k_apply_dist    E = TB * Sel from the gathered rows -> ebuf (for the sweep);
- *                   the shard that owned the j-th elected row stores E_j in place;
- *   k_sweep         unchanged, on the local active rows.
+ *   k_select_publish  each shard reduces ITS active rows' panel words to <= 64
+ *                     candidate rows (a basis of their span) and STORES the
+ *                     candidates' raw panel words + row numbers into every
+ *                     peer's exchange block, then signals flag A (release.sys);
+ *   k_elect           waits for all peers' flag A (acquire.sys), then every shard
+ *                     runs the same deterministic election over the G*64
+ *                     candidates (priority rotates with w so rows deplete
+ *                     evenly): the elected rows' pivot columns are the panel's
+ *                     GLOBAL column rank profile -- what _mzd_pluq reports in Q
+ *                     (reference _internal.c:433) -- because the
+ *                     union of the local bases spans the global active row space;
+ *   k_apply_pull      E = TB * Sel where the elected rows Sel are LOADED straight
+ *                     from their owners' matrices over NVLink (the north star's
+ *                     "broadcast of each pivot row", pulled by the consumers)
+ *                     -> local ebuf for the sweep;
+ *   k_peer_barrier    flag B: nobody overwrites an elected row before every
+ *                     peer has pulled it;
+ *   k_apply_commit    the shard that owned the j-th elected row stores E_j in its
+ *                     place; displaced rows move to the vacated positions;
+ *   k_sweep           unchanged, on the local active rows.
+ *
+ * On a loopback context (all shards on one GPU, one stream) the same kernels run
+ * phase by phase in stream order and the flag waits are skipped.
  *
  * Back-substitution (k_bs_outer / k_bs_inner) is a blocked triangular solve over
  * super-panels of BS_S panel words; see the comments at those kernels.
@@ -30,60 +40,110 @@
 
 namespace gf2b200 {
 
-#define CAND_W 66 /* words per shard in exchange 1: count, 64 panel words, pad */
+#define MAX_SHARDS 64
+#define CAND_W 104 /* words a shard publishes per panel: count, 64 panel words, 64 row numbers (32 words), pad */
+
+/* Exchange block of one shard; lives right behind its matrix in the same
+ * allocation so one IPC handle maps both.  Slot [src] is written by shard src. */
+struct XchBlock {
+	unsigned flagA[MAX_SHARDS]; /* epoch of the last candidate block published by src */
+	unsigned flagB[MAX_SHARDS]; /* epoch up to which src has pulled its pivot rows */
+	u64 cand[MAX_SHARDS][CAND_W];
+};
+
+/* Peer mappings of one shard (device resident). */
+struct PeerTable {
+	u64 *base[MAX_SHARDS];       /* strip-major matrices (self included) */
+	XchBlock *xch[MAX_SHARDS];
+	long long mp[MAX_SHARDS];    /* padded row counts (strip stride) */
+};
 
 /* Per-shard description of its share of the current panel (written by k_elect). */
 struct DistPanel {
-	int my_cnt;        /* elected rows owned by this shard */
-	int my_row[64];    /* local row of my i-th elected row (before the moves) */
-	int my_slot[64];   /* candidate slot it is sent in */
+	int my_cnt;          /* elected rows owned by this shard */
+	int my_row[64];      /* local row of my i-th elected row (before the moves) */
 	int my_idx_of_j[64]; /* for E row j (pivot-column rank): index i among mine, or -1 */
+	int src[64];         /* elected row j: owner shard ... */
+	int srow[64];        /* ... and its row number there */
 };
 
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+	unsigned v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+/* spin until *flag >= epoch (epochs only grow); gives up after ~4 s and reports a fault */
+__device__ __forceinline__ bool wait_flag(const unsigned *flag, unsigned epoch) {
+	const unsigned long long t0 = globaltimer_ns();
+	while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+		if (globaltimer_ns() - t0 > 4000000000ULL) return false;
+		__nanosleep(64);
+	}
+	return true;
+}
+
 /* ------------------------------------------------------------------------
- * k_select_local: candidates of one shard for panel word w.
- * cand[0] = count, cand[1 + l] = raw panel word of the l-th candidate row;
- * selrow[l] = its local row.
+ * k_select_publish: candidates of one shard for the current panel word, stored
+ * into every peer's exchange block (slot `me`), then flag A.
+ * block = [count | 64 raw panel words | 64 local row numbers as ints | pad]
  * ---------------------------------------------------------------------- */
 __global__ void __launch_bounds__(SEL_THREADS, 1)
-k_select_local(Mat M, const u64 *__restrict__ pc, u64 colmask, const SolverState *st,
-               u64 *__restrict__ cand, int *__restrict__ selrow) {
+k_select_publish(Mat M, const u64 *__restrict__ pc, u64 colmask, const SolverState *st,
+                 const PeerTable *__restrict__ pt, int me, int G, unsigned epoch, int barriers) {
 	__shared__ SelectSmem S;
+	__shared__ u64 blk[CAND_W];
 	const int tid = threadIdx.x;
-	if (tid < 64) {
-		S.B[tid] = 0;
-		S.TB[tid] = 0;
-		S.sel[tid] = -1;
-	}
-	if (tid == 0) {
-		S.pm = 0;
-		S.nsel = 0;
-	}
+	select_init(S);
 	__syncthreads();
 	select_scan(S, pc, st->r_loc, M.m, colmask);
+	if (tid < CAND_W) blk[tid] = 0;
+	__syncthreads();
 	if (tid < 64) {
 		const int n = S.nsel;
-		cand[1 + tid] = (tid < n) ? (pc[S.sel[tid]] & colmask) : 0;
-		selrow[tid] = (tid < n) ? S.sel[tid] : -1;
-		if (tid == 0) {
-			cand[0] = (u64)n;
-			cand[65] = 0;
+		if (tid < n) {
+			blk[1 + tid] = pc[S.sel[tid]] & colmask;
+			reinterpret_cast<int *>(blk + 65)[tid] = S.sel[tid];
 		}
+		if (tid == 0) blk[0] = (u64)n;
 	}
+	__syncthreads();
+	for (int t = tid; t < G * CAND_W; t += SEL_THREADS) {
+		const int g = t / CAND_W, i = t - g * CAND_W;
+		pt->xch[g]->cand[me][i] = blk[i];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (barriers && tid < G) st_release_sys(&pt->xch[tid]->flagA[me], epoch);
 }
 
 /* ------------------------------------------------------------------------
  * k_elect: global pivot election, one warp, identical on every shard.
- * cand_all = G blocks of CAND_W words.  Candidate code = shard * 64 + slot.
+ * Candidate code = shard * 64 + slot.
  * ---------------------------------------------------------------------- */
 __global__ void __launch_bounds__(32)
-k_elect(const u64 *__restrict__ cand_all, int G, int me, int w, u64 colmask, SolverState *st,
-        PanelDesc *pd, DistPanel *dp, const int *__restrict__ selrow, u64 *__restrict__ pc,
-        long long *hist_r, u64 *hist_pm, unsigned char *hist_owner) {
+k_elect(const XchBlock *__restrict__ xch, int G, int me, int w, u64 colmask, SolverState *st,
+        PanelDesc *pd, DistPanel *dp, u64 *__restrict__ pc, long long *hist_r, u64 *hist_pm,
+        unsigned char *hist_owner, unsigned epoch, int barriers) {
 	__shared__ u64 B[64], TB[64];
 	__shared__ int sel[64];
 	__shared__ int topsel[64], mv_src[64], mv_dst[64];
 	const int lane = threadIdx.x;
+	if (barriers) {
+		bool ok = true;
+		for (int g = lane; g < G; g += 32) ok = ok && wait_flag(&xch->flagA[g], epoch);
+		if (!__all_sync(0xffffffffu, ok)) {
+			if (lane == 0) st->fault = 1;
+			return;
+		}
+	}
 	for (int c = lane; c < 64; c += 32) {
 		sel[c] = -1;
 		topsel[c] = 0;
@@ -95,7 +155,7 @@ k_elect(const u64 *__restrict__ cand_all, int G, int me, int w, u64 colmask, Sol
 	W.nsel = 0;
 	for (int jj = 0; jj < G && W.pm != colmask; jj++) {
 		const int src = (w + jj) % G;
-		const u64 *cb = cand_all + (long long)src * CAND_W;
+		const u64 *cb = xch->cand[src];
 		const int cnt = (int)cb[0];
 		/* lanes fetch 32 candidates at a time; each is then broadcast and inserted */
 		for (int q0 = 0; q0 < cnt && W.pm != colmask; q0 += 32) {
@@ -108,14 +168,17 @@ k_elect(const u64 *__restrict__ cand_all, int G, int me, int w, u64 colmask, Sol
 	wb_store(W, B, TB, lane);
 	__syncwarp();
 	const u64 pm = W.pm;
-	const int nsel = W.nsel;
-	const int k = nsel;
+	const int k = W.nsel;
 	const long long r_loc = st->r_loc;
 	for (int c = lane; c < 64; c += 32) {
 		pd->TB[c] = ((pm >> c) & 1) ? TB[c] : 0;
 		pd->sel[c] = sel[c];
-		hist_owner[(long long)w * 64 + c] = (c < k) ? (unsigned char)(sel[c] >> 6) : 0xFF;
+		const int src = (c < k) ? (sel[c] >> 6) : -1;
+		dp->src[c] = src;
+		dp->srow[c] = (c < k) ? reinterpret_cast<const int *>(xch->cand[src] + 65)[sel[c] & 63] : -1;
+		hist_owner[(long long)w * 64 + c] = (c < k) ? (unsigned char)src : 0xFF;
 	}
+	__syncwarp();
 	/* my share, in election order */
 	int my_cnt = 0;
 	for (int h = 0; h < 2; h++) {
@@ -124,8 +187,7 @@ k_elect(const u64 *__restrict__ cand_all, int G, int me, int w, u64 colmask, Sol
 		const unsigned bal = __ballot_sync(0xffffffffu, mine);
 		const int i = my_cnt + __popc(bal & ((1u << lane) - 1));
 		if (mine) {
-			dp->my_row[i] = selrow[sel[j] & 63];
-			dp->my_slot[i] = sel[j] & 63;
+			dp->my_row[i] = dp->srow[j];
 			dp->my_idx_of_j[j] = i;
 		} else {
 			dp->my_idx_of_j[j] = -1;
@@ -133,7 +195,6 @@ k_elect(const u64 *__restrict__ cand_all, int G, int me, int w, u64 colmask, Sol
 		my_cnt += __popc(bal);
 	}
 	__syncwarp();
-	__threadfence_block();
 	/* local rows r_loc .. r_loc+my_cnt-1 become this shard's echelon rows */
 	for (int i = lane; i < my_cnt; i += 32) {
 		const int row = dp->my_row[i];
@@ -181,51 +242,31 @@ k_elect(const u64 *__restrict__ cand_all, int G, int me, int w, u64 colmask, Sol
 	}
 }
 
-/* my elected rows, strips [s0, ns) -> send slab [slot][strip - s0][64 B] */
+/* ------------------------------------------------------------------------
+ * k_apply_pull: per strip s >= s0: pull the k elected rows' 64-byte pieces from
+ * their owners' matrices (peer loads), E_c = XOR_{j in TB[c]} Sel_j -> ebuf[s][c].
+ * Nothing is written to any matrix here.
+ * ---------------------------------------------------------------------- */
 __global__ void __launch_bounds__(256)
-k_pack(Mat M, const DistPanel *__restrict__ dp, uint4 *__restrict__ rows_send, int s0) {
-	const int cnt = dp->my_cnt;
-	const int tid = threadIdx.x, rr = tid >> 2, ch = tid & 3;
-	if (rr >= cnt) return;
-	const int row = dp->my_row[rr], slot = dp->my_slot[rr];
-	const int nsr = M.ns - s0;
-	const uint4 *mb = reinterpret_cast<const uint4 *>(M.base);
-	for (int s = s0 + blockIdx.x; s < M.ns; s += gridDim.x)
-		rows_send[((long long)slot * nsr + (s - s0)) * 4 + ch] = mb[((long long)s * M.mp + row) * 4 + ch];
-}
-
-/* k_apply for gathered rows: rows_all = [G*64 codes][ns - s0][64 B] */
-__global__ void __launch_bounds__(256)
-k_apply_dist(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restrict__ dp,
-             const uint4 *__restrict__ rows_all, uint4 *__restrict__ ebuf, int s0) {
+k_apply_pull(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restrict__ dp,
+             const PeerTable *__restrict__ pt, uint4 *__restrict__ ebuf, int s0) {
 	__shared__ uint4 Sel[64][4];
-	__shared__ uint4 Dis[64][4];
 	__shared__ u64 sTB[64];
-	__shared__ int scode[64], ssrc[64], sdst[64], smyidx[64];
 	const int k = pd->k;
 	if (k == 0) return;
 	const int tid = threadIdx.x, rr = tid >> 2, ch = tid & 3;
-	const long long r = pd->r;
-	const int nmove = pd->nmove;
-	const u64 pm = pd->pm;
-	if (tid < 64) {
-		sTB[tid] = pd->TB[tid];
-		scode[tid] = pd->sel[tid];
-		ssrc[tid] = pd->mv_src[tid];
-		sdst[tid] = pd->mv_dst[tid];
-		smyidx[tid] = dp->my_idx_of_j[tid];
+	if (tid < 64) sTB[tid] = pd->TB[tid];
+	const uint4 *prow = nullptr; /* my elected row's piece of strip 0 on its owner */
+	long long pstride = 0;       /* uint4 per strip there */
+	if (rr < k) {
+		const int src = dp->src[rr];
+		pstride = pt->mp[src] * 4;
+		prow = reinterpret_cast<const uint4 *>(pt->base[src]) + (long long)dp->srow[rr] * 4 + ch;
 	}
 	__syncthreads();
-	uint4 *mb = reinterpret_cast<uint4 *>(M.base);
-	const int nsr = M.ns - s0;
-	const bool ispiv = (pm >> rr) & 1;
-	const int jrank = __popcll(pm & ((1ULL << rr) - 1));
-	const int myi = ispiv ? smyidx[jrank] : -1;
+	const uint4 z = make_uint4(0, 0, 0, 0);
 	for (int s = s0 + blockIdx.x; s < M.ns; s += gridDim.x) {
-		const long long sb = (long long)s * M.mp;
-		uint4 z = make_uint4(0, 0, 0, 0);
-		Sel[rr][ch] = (rr < k) ? rows_all[((long long)scode[rr] * nsr + (s - s0)) * 4 + ch] : z;
-		if (rr < nmove) Dis[rr][ch] = mb[(sb + ssrc[rr]) * 4 + ch];
+		Sel[rr][ch] = (rr < k) ? __ldcg(prow + (long long)s * pstride) : z;
 		__syncthreads();
 		uint4 acc = z;
 		u64 t = sTB[rr];
@@ -235,7 +276,53 @@ k_apply_dist(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restric
 			xor4(acc, Sel[l][ch]);
 		}
 		ebuf[(long long)s * 256 + rr * 4 + ch] = acc;
-		if (myi >= 0) mb[(sb + r + myi) * 4 + ch] = acc;
+		__syncthreads();
+	}
+}
+
+/* flag B: signal "I have pulled my pivot rows of this panel" to every peer and
+ * wait until every peer has done the same */
+__global__ void __launch_bounds__(64)
+k_peer_barrier(XchBlock *xch, const PeerTable *__restrict__ pt, int me, int G, unsigned epoch,
+               SolverState *st) {
+	const int g = threadIdx.x;
+	__threadfence_system();
+	bool ok = true;
+	if (g < G) {
+		st_release_sys(&pt->xch[g]->flagB[me], epoch);
+		ok = wait_flag(&xch->flagB[g], epoch);
+	}
+	if (!ok) st->fault = 1;
+}
+
+/* k_apply_commit: the owner of elected row j stores E_j (from ebuf) at local row
+ * r + (index among its own); displaced rows go to the vacated positions */
+__global__ void __launch_bounds__(256)
+k_apply_commit(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restrict__ dp,
+               const uint4 *__restrict__ ebuf, int s0) {
+	__shared__ uint4 Dis[64][4];
+	__shared__ int ssrc[64], sdst[64], smyidx[64];
+	const int k = pd->k;
+	if (k == 0) return;
+	const int tid = threadIdx.x, rr = tid >> 2, ch = tid & 3;
+	const long long r = pd->r;
+	const int nmove = pd->nmove;
+	const u64 pm = pd->pm;
+	if (tid < 64) {
+		ssrc[tid] = pd->mv_src[tid];
+		sdst[tid] = pd->mv_dst[tid];
+		smyidx[tid] = dp->my_idx_of_j[tid];
+	}
+	__syncthreads();
+	uint4 *mb = reinterpret_cast<uint4 *>(M.base);
+	const bool ispiv = (pm >> rr) & 1;
+	const int jrank = __popcll(pm & ((1ULL << rr) - 1));
+	const int myi = ispiv ? smyidx[jrank] : -1;
+	for (int s = s0 + blockIdx.x; s < M.ns; s += gridDim.x) {
+		const long long sb = (long long)s * M.mp;
+		if (rr < nmove) Dis[rr][ch] = mb[(sb + ssrc[rr]) * 4 + ch];
+		__syncthreads();
+		if (myi >= 0) mb[(sb + r + myi) * 4 + ch] = ebuf[(long long)s * 256 + rr * 4 + ch];
 		if (rr < nmove) mb[(sb + sdst[rr]) * 4 + ch] = Dis[rr][ch];
 		__syncthreads();
 	}

@@ -67,7 +67,7 @@ struct SolverState {
 	long long r;     /* current (global) rank */
 	long long r_loc; /* first active row of this shard (== r on a single GPU) */
 	int inconsistent;
-	int pad;
+	int fault;       /* a peer-memory flag wait timed out */
 };
 
 __host__ __device__ __forceinline__ u64 mix64(u64 z) {
