@@ -14,7 +14,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libgf2b200.so"
+LIB_PATH = Path(os.environ.get("GF2B200_LIB") or (_HERE / "libgf2b200.so"))
 
 OK, INCONSISTENT = 0, 1
 

@@ -313,7 +313,7 @@ extern "C" void gf2b200_system_destroy(gf2b200_system *sys) {
 static cudaError_t shard_alloc(Shard &s, int world) {
 	const Mat &M = s.M;
 	/* matrix + (sharded) exchange block in ONE allocation */
-	const size_t mat_bytes = (size_t)M.ns * (size_t)M.mp * 64;
+	const size_t mat_bytes = (size_t)M.ns * (size_t)M.mp * SBYTES;
 	cudaError_t e = cudaMalloc(&s.M.base, mat_bytes + (world > 1 ? sizeof(XchBlock) : 0));
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_pc[0], (size_t)M.mp * 8);
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_pc[1], (size_t)M.mp * 8);
@@ -321,7 +321,7 @@ static cudaError_t shard_alloc(Shard &s, int world) {
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_pd, 2 * sizeof(PanelDesc));
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_hist_r, (size_t)M.nw * 8);
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_hist_pm, (size_t)M.nw * 8);
-	if (e == cudaSuccess) e = cudaMalloc(&s.d_ebuf, (size_t)M.ns * 4096);
+	if (e == cudaSuccess) e = cudaMalloc(&s.d_ebuf, (size_t)M.ns * EBUF_Q * 16);
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_x, (size_t)(M.nw + 1) * 8);
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_slab, (size_t)BS_S * 64 * BS_W * 8);
 	s.d_slab_all = s.d_slab;
@@ -364,7 +364,7 @@ static int map_peers(gf2b200_system *sys) {
 		return GF2B200_OK;
 	}
 	Shard &h = sys->sh[0];
-	const size_t mat_bytes = (size_t)h.M.ns * (size_t)h.M.mp * 64;
+	const size_t mat_bytes = (size_t)h.M.ns * (size_t)h.M.mp * SBYTES;
 	cudaIpcMemHandle_t mine;
 	CK(ctx, cudaIpcGetMemHandle(&mine, h.M.base));
 	std::vector<cudaIpcMemHandle_t> all((size_t)G);
@@ -392,7 +392,7 @@ static int map_peers(gf2b200_system *sys) {
 		}
 		pt.base[g] = (u64 *)p;
 		/* the peer's exchange block sits behind ITS matrix: ns is global, mp is per shard */
-		pt.xch[g] = reinterpret_cast<XchBlock *>((char *)p + (size_t)h.M.ns * (size_t)pt.mp[g] * 64);
+		pt.xch[g] = reinterpret_cast<XchBlock *>((char *)p + (size_t)h.M.ns * (size_t)pt.mp[g] * SBYTES);
 	}
 	(void)mat_bytes;
 	CK(ctx, cudaMemcpy(h.d_pt, &pt, sizeof pt, cudaMemcpyHostToDevice));
@@ -426,7 +426,7 @@ extern "C" int gf2b200_system_create(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2
 		M.m = r1 - r0;
 		M.n = n;
 		M.nw = (int)((n + 63) / 64);
-		M.ns = (M.nw + 1 + 7) / 8;
+		M.ns = (M.nw + 1 + SW - 1) / SW;
 		M.mp = (std::max<long long>(M.m, 1) + 15) / 16 * 16;
 		h.d_pc[0] = h.d_pc[1] = nullptr;
 		h.d_state = nullptr; h.d_pd = nullptr; h.d_hist_r = nullptr; h.d_hist_pm = nullptr;
@@ -477,7 +477,7 @@ extern "C" int gf2b200_system_load_device(gf2b200_system *sys, const uint64_t *d
 	const long long base = sys->sh[0].row_begin; /* dA / db start at the first local row */
 	for (Shard &h : sys->sh) {
 		if (h.M.m == 0) continue;
-		long long total = h.M.m * h.M.ns * 8;
+		long long total = h.M.m * h.M.ns * SW;
 		long long off = h.row_begin - base;
 		k_layout<<<grid_for(total, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
 		    h.M, (const u64 *)dA + off * stride64, (const u64 *)db, stride64, 0, h.M.m, off);
@@ -529,7 +529,7 @@ extern "C" int gf2b200_system_load_host(gf2b200_system *sys, const uint64_t *A, 
 			if (e == cudaSuccess) e = cudaEventRecord(copied[bi], copy_stream);
 			if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, copied[bi], 0);
 			if (e != cudaSuccess) break;
-			long long total = nr * h.M.ns * 8;
+			long long total = nr * h.M.ns * SW;
 			k_layout<<<grid_for(total, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
 			    h.M, stage[bi], d_b, stride64, row0, nr, off + row0);
 			e = cudaGetLastError();
@@ -562,7 +562,7 @@ extern "C" int gf2b200_system_generate(gf2b200_system *sys, uint64_t seed) {
 	for (Shard &h : sys->sh) {
 		const Mat &M = h.M;
 		if (M.m == 0) continue;
-		long long total = M.m * M.ns * 8;
+		long long total = M.m * M.ns * SW;
 		k_generate<<<grid_for(total, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(M, seed, h.row_begin);
 		/* x* goes through d_x (overwritten later by the solve) */
 		k_synth_xstar<<<(M.nw + 255) / 256, 256, 0, ctx->stream>>>(h.d_x, M.nw, M.n, seed);
@@ -614,10 +614,11 @@ static int forward_single(gf2b200_system *sys, long long *launches) {
 		u64 colmask_next = ~0ULL;
 		if (w + 1 == nw - 1 && (M.n & 63)) colmask_next = (1ULL << (M.n & 63)) - 1;
 		k_select<<<1, SEL_THREADS, 0, st>>>(M, pc_cur, w, colmask, h.d_state, pd, h.d_hist_r, h.d_hist_pm);
-		int s0a = w >> 3;
-		k_apply<<<std::min(M.ns - s0a, apply_cap), 256, 0, st>>>(M, pd, h.d_ebuf, s0a);
+		int s0a = w >> SW_SHIFT;
+		k_apply<<<std::min(M.ns - s0a, apply_cap), APPLY_THREADS, 0, st>>>(M, pd, h.d_ebuf, s0a);
 		if (prof) CK(ctx, cudaEventRecord(sys->ev[4 + 2 * w], st));
-		k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(M, pd, pc_cur, pc_next, h.d_ebuf, w, (w + 1) >> 3,
+		k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(M, pd, pc_cur, pc_next, h.d_ebuf, w,
+		                                                     (w + 1) >> SW_SHIFT,
 		                                                     pdn, h.d_state, h.d_hist_r, h.d_hist_pm, colmask_next);
 		if (prof) CK(ctx, cudaEventRecord(sys->ev[5 + 2 * w], st));
 		*launches += 3;
@@ -645,7 +646,7 @@ static int forward_sharded(gf2b200_system *sys, long long *launches, double *xby
 	for (int w = 0; w < nw; w++) {
 		u64 colmask = ~0ULL;
 		if (w == nw - 1 && (sys->n & 63)) colmask = (1ULL << (sys->n & 63)) - 1;
-		const int s0a = w >> 3, nsr = ns - s0a;
+		const int s0a = w >> SW_SHIFT, nsr = ns - s0a;
 		const unsigned epoch = sys->epoch_base + (unsigned)w + 1;
 		for (Shard &h : sys->sh)
 			k_select_publish<<<1, SEL_THREADS, 0, st>>>(h.M, h.d_pc[w & 1], colmask, h.d_state, h.d_pt, h.index, G,
@@ -654,7 +655,7 @@ static int forward_sharded(gf2b200_system *sys, long long *launches, double *xby
 			k_elect<<<1, 32, 0, st>>>(h.xch, G, h.index, w, colmask, h.d_state, h.d_pd, h.d_dp, h.d_pc[w & 1],
 			                          h.d_hist_r, h.d_hist_pm, h.d_hist_owner, epoch, barriers);
 		for (Shard &h : sys->sh)
-			k_apply_pull<<<std::min(nsr, apply_cap), 256, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_pt, h.d_ebuf, s0a);
+			k_apply_pull<<<std::min(nsr, apply_cap), APPLY_THREADS, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_pt, h.d_ebuf, s0a);
 		if (barriers)
 			for (Shard &h : sys->sh) {
 				k_peer_barrier<<<1, 64, 0, st>>>(h.xch, h.d_pt, h.index, G, epoch, h.d_state);
@@ -662,18 +663,18 @@ static int forward_sharded(gf2b200_system *sys, long long *launches, double *xby
 			}
 		int li = 0;
 		for (Shard &h : sys->sh) {
-			k_apply_commit<<<std::min(nsr, apply_cap), 256, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_ebuf, s0a);
+			k_apply_commit<<<std::min(nsr, apply_cap), APPLY_THREADS, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_ebuf, s0a);
 			const bool ev = prof && li == 0;
 			if (ev) CK(ctx, cudaEventRecord(sys->ev[4 + 2 * w], st));
 			k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(h.M, h.d_pd, h.d_pc[w & 1],
-			                                                     h.d_pc[(w + 1) & 1], h.d_ebuf, w, (w + 1) >> 3,
-			                                                     nullptr, nullptr, nullptr, nullptr, 0);
+			                                                     h.d_pc[(w + 1) & 1], h.d_ebuf, w,
+			                                                     (w + 1) >> SW_SHIFT, nullptr, nullptr, nullptr, nullptr, 0);
 			if (ev) CK(ctx, cudaEventRecord(sys->ev[5 + 2 * w], st));
 			li++;
 		}
 		*launches += 5 * (long long)sys->sh.size();
 		/* per shard: candidate blocks stored to G peers + 64 pivot-row pieces pulled per strip */
-		*xbytes += (double)sys->sh.size() * ((double)G * CAND_W * 8 + 64.0 * nsr * 64.0);
+		*xbytes += (double)sys->sh.size() * ((double)G * CAND_W * 8 + 64.0 * nsr * SBYTES);
 	}
 	sys->epoch_base += (unsigned)nw;
 	for (Shard &h : sys->sh) {
@@ -808,7 +809,7 @@ extern "C" int gf2b200_system_eliminate(gf2b200_system *sys) {
 			}
 			const long long r1 = h.hist_r[w] + mine;
 			if (k == 0 || r1 >= h.M.m) continue;
-			double bytes = 2.0 * (double)(h.M.m - r1) * 64.0 * (double)(ns - ((w + 1) >> 3));
+			double bytes = 2.0 * (double)(h.M.m - r1) * (double)SBYTES * (double)(ns - ((w + 1) >> SW_SHIFT));
 			S.sweep_bytes += bytes;
 			S.sweep_launches++;
 			if (prof && l == 0) {
@@ -877,7 +878,7 @@ extern "C" int gf2b200_system_result(gf2b200_system *sys, int mode, gf2b200_resu
 			gf2b200_result_free(out);
 			return fail(ctx, GF2B200_ENOMEM, "malloc basis");
 		}
-		size_t xs_bytes = (size_t)M.ns * 64;
+		size_t xs_bytes = (size_t)M.ns * SBYTES;
 		if (xs_bytes > 200 * 1024) {
 			gf2b200_result_free(out);
 			return fail(ctx, GF2B200_EINVAL, "n too large for the kernel-basis back-substitution kernel");

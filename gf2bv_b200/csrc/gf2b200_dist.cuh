@@ -243,25 +243,25 @@ k_elect(const XchBlock *__restrict__ xch, int G, int me, int w, u64 colmask, Sol
 }
 
 /* ------------------------------------------------------------------------
- * k_apply_pull: per strip s >= s0: pull the k elected rows' 64-byte pieces from
+ * k_apply_pull: per strip s >= s0: pull the k elected rows' 128-byte pieces from
  * their owners' matrices (peer loads), E_c = XOR_{j in TB[c]} Sel_j -> ebuf[s][c].
  * Nothing is written to any matrix here.
  * ---------------------------------------------------------------------- */
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(APPLY_THREADS)
 k_apply_pull(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restrict__ dp,
              const PeerTable *__restrict__ pt, uint4 *__restrict__ ebuf, int s0) {
-	__shared__ uint4 Sel[64][4];
+	__shared__ uint4 Sel[64][SQ];
 	__shared__ u64 sTB[64];
 	const int k = pd->k;
 	if (k == 0) return;
-	const int tid = threadIdx.x, rr = tid >> 2, ch = tid & 3;
+	const int tid = threadIdx.x, rr = tid / SQ, ch = tid % SQ;
 	if (tid < 64) sTB[tid] = pd->TB[tid];
 	const uint4 *prow = nullptr; /* my elected row's piece of strip 0 on its owner */
 	long long pstride = 0;       /* uint4 per strip there */
 	if (rr < k) {
 		const int src = dp->src[rr];
-		pstride = pt->mp[src] * 4;
-		prow = reinterpret_cast<const uint4 *>(pt->base[src]) + (long long)dp->srow[rr] * 4 + ch;
+		pstride = pt->mp[src] * SQ;
+		prow = reinterpret_cast<const uint4 *>(pt->base[src]) + (long long)dp->srow[rr] * SQ + ch;
 	}
 	__syncthreads();
 	const uint4 z = make_uint4(0, 0, 0, 0);
@@ -275,7 +275,7 @@ k_apply_pull(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restric
 			t &= t - 1;
 			xor4(acc, Sel[l][ch]);
 		}
-		ebuf[(long long)s * 256 + rr * 4 + ch] = acc;
+		ebuf[(long long)s * EBUF_Q + rr * SQ + ch] = acc;
 		__syncthreads();
 	}
 }
@@ -297,14 +297,14 @@ k_peer_barrier(XchBlock *xch, const PeerTable *__restrict__ pt, int me, int G, u
 
 /* k_apply_commit: the owner of elected row j stores E_j (from ebuf) at local row
  * r + (index among its own); displaced rows go to the vacated positions */
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(APPLY_THREADS)
 k_apply_commit(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restrict__ dp,
                const uint4 *__restrict__ ebuf, int s0) {
-	__shared__ uint4 Dis[64][4];
+	__shared__ uint4 Dis[64][SQ];
 	__shared__ int ssrc[64], sdst[64], smyidx[64];
 	const int k = pd->k;
 	if (k == 0) return;
-	const int tid = threadIdx.x, rr = tid >> 2, ch = tid & 3;
+	const int tid = threadIdx.x, rr = tid / SQ, ch = tid % SQ;
 	const long long r = pd->r;
 	const int nmove = pd->nmove;
 	const u64 pm = pd->pm;
@@ -320,10 +320,10 @@ k_apply_commit(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restr
 	const int myi = ispiv ? smyidx[jrank] : -1;
 	for (int s = s0 + blockIdx.x; s < M.ns; s += gridDim.x) {
 		const long long sb = (long long)s * M.mp;
-		if (rr < nmove) Dis[rr][ch] = mb[(sb + ssrc[rr]) * 4 + ch];
+		if (rr < nmove) Dis[rr][ch] = mb[(sb + ssrc[rr]) * SQ + ch];
 		__syncthreads();
-		if (myi >= 0) mb[(sb + r + myi) * 4 + ch] = ebuf[(long long)s * 256 + rr * 4 + ch];
-		if (rr < nmove) mb[(sb + sdst[rr]) * 4 + ch] = Dis[rr][ch];
+		if (myi >= 0) mb[(sb + r + myi) * SQ + ch] = ebuf[(long long)s * EBUF_Q + rr * SQ + ch];
+		if (rr < nmove) mb[(sb + sdst[rr]) * SQ + ch] = Dis[rr][ch];
 		__syncthreads();
 	}
 }
@@ -342,7 +342,7 @@ k_apply_commit(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restr
  *   k_bs_inner  (one CTA, identical on every shard) solves the BS_S-word
  *               triangular block panel by panel and writes x[P*BS_S ..].
  * ---------------------------------------------------------------------- */
-#define BS_S 32 /* panel words per super-panel (4 strips) */
+#define BS_S 32 /* panel words per super-panel (2 strips) */
 #define BS_W 40 /* slab row: BS_S words, then y at [BS_S], padding */
 
 __global__ void __launch_bounds__(256)
@@ -372,13 +372,13 @@ k_bs_outer(Mat M, const long long *__restrict__ hist_r, const u64 *__restrict__ 
 		for (int l = lane; l < BS_W; l += 32) out[l] = 0;
 		return;
 	}
-	/* outer part: strips beyond the super-panel, 8 lanes per 64-byte piece */
-	const int wl = lane & 7, so = lane >> 3;
-	const u64 *rowp = M.base + row * 8 + wl;
+	/* outer part: strips beyond the super-panel, SW lanes per 128-byte piece */
+	const int wl = lane & (SW - 1), so = lane >> SW_SHIFT;
+	const u64 *rowp = M.base + row * SW + wl;
 	u64 acc = 0;
-	for (int s = (P + 1) * (BS_S / 8) + so; s < M.ns; s += 4) {
-		const int wd = s * 8 + wl;
-		if (wd <= M.nw) acc ^= rowp[(long long)s * M.mp * 8] & x[wd];
+	for (int s = (P + 1) * (BS_S / SW) + so; s < M.ns; s += 32 / SW) {
+		const int wd = s * SW + wl;
+		if (wd <= M.nw) acc ^= rowp[(long long)s * M.mp * SW] & x[wd];
 	}
 	int par = __popcll(acc) & 1;
 	par = __reduce_xor_sync(0xffffffffu, par);

@@ -8,11 +8,12 @@
  * 64-column panels designed around HBM streaming:
  *
  *   HBM layout ("strip-major"): the augmented matrix [A | b] is cut into column
- *   strips of 8 words (64 B).  Strip s holds, for every row i, the 64-byte piece
- *   words 8s..8s+7 of that row, rows contiguous:  word(i, w) lives at
- *       base[((w / 8) * mp + i) * 8 + (w % 8)].
- *   A sweep work unit (one strip x 1024 rows) is therefore ONE contiguous 64 KiB
- *   region: perfectly coalesced 128-bit loads/stores, no strided DRAM pages.
+ *   strips of SW = 16 words (128 B).  Strip s holds, for every row i, the 128-byte
+ *   piece words 16s..16s+15 of that row, rows contiguous:  word(i, w) lives at
+ *       base[((w / 16) * mp + i) * 16 + (w % 16)].
+ *   A sweep work unit (one strip x 512 rows) is therefore ONE contiguous 64 KiB
+ *   region: perfectly coalesced 128-bit loads/stores, no strided DRAM pages, and a
+ *   row piece is exactly one 128-byte shared-memory line of the lookup tables.
  *   b sits alone in word nw (bit 0).
  *
  *   per panel (word column w):
@@ -23,11 +24,11 @@
  *               64x64 transform TB that turns the selected rows into RREF.
  *     k_apply   per strip: E = TB * Sel (reduced pivot rows), stores them at rows
  *               r..r+k-1 (physical swap with the displaced rows) and into the
- *               L2-resident staging tile ebuf[s] (64 x 64 B, indexed by column).
+ *               L2-resident staging tile ebuf[s] (64 x 128 B, indexed by column).
  *     k_sweep   persistent, 1 CTA / SM: TMA bulk-copies ebuf[s] into shared
- *               memory, builds eight 256-entry Four-Russians tables (128 KiB),
- *               then streams every active row piece: 8 table XORs per 16 B.
- *               This is the HBM-bound kernel (2 * rows * 64 B per strip).
+ *               memory, builds nine Four-Russians tables (160 KiB of 128-byte
+ *               lines), then streams every active row piece: 9 table XORs per
+ *               16 B.  This is the HBM-bound kernel (2 * rows * 128 B per strip).
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -39,13 +40,18 @@ typedef unsigned long long u64;
 
 #define GF2_PHI 0x9E3779B97F4A7C15ULL
 
+#define SW 16        /* 64-bit words per strip piece */
+#define SW_SHIFT 4
+#define SQ 8         /* 16-byte chunks per strip piece */
+#define SBYTES 128   /* bytes per strip piece */
+
 struct Mat {
-	u64 *base;      /* strip-major storage, ns * mp * 8 words */
+	u64 *base;      /* strip-major storage, ns * mp * SW words */
 	long long mp;   /* padded row count (multiple of 16) */
 	long long m;    /* rows held here */
 	long long n;    /* unknowns */
 	int nw;         /* ceil(n / 64): A words per row */
-	int ns;         /* strips: ceil((nw + 1) / 8) */
+	int ns;         /* strips: ceil((nw + 1) / SW) */
 };
 
 /* Device-resident description of the current panel (written by k_select). */
@@ -78,7 +84,7 @@ __host__ __device__ __forceinline__ u64 mix64(u64 z) {
 }
 
 __device__ __forceinline__ long long widx(const Mat &M, long long i, int w) {
-	return ((long long)(w >> 3) * M.mp + i) * 8 + (w & 7);
+	return ((long long)(w >> SW_SHIFT) * M.mp + i) * SW + (w & (SW - 1));
 }
 
 __device__ __forceinline__ u64 shfl64(u64 v, int src) {
@@ -90,11 +96,11 @@ __device__ __forceinline__ u64 shfl64(u64 v, int src) {
 /* ------------------------------------------------------------------------
  * Loading: row-major words -> strip-major, masking bits >= n (the reference
  * ignores them, _internal.c:45,48) and placing b (bit i of the packed b) in
- * word nw.  One thread per (row, word); 8 consecutive lanes write one 64 B piece.
+ * word nw.  One thread per (row, word); 16 consecutive lanes write one 128 B piece.
  * ---------------------------------------------------------------------- */
 __global__ void k_layout(Mat M, const u64 *__restrict__ src, const u64 *__restrict__ bsrc,
                          long long stride, long long row0, long long nrows, long long brow0) {
-	const int WT = M.ns * 8;
+	const int WT = M.ns * SW;
 	long long total = nrows * WT;
 	for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
 	     t += (long long)gridDim.x * blockDim.x) {
@@ -115,7 +121,7 @@ __global__ void k_layout(Mat M, const u64 *__restrict__ src, const u64 *__restri
 /* Synthetic dense system of SURVEY.md 8(d): word(i, w) = mix(seed + PHI*(i*nw + w + 1)),
  * i = GLOBAL row index (grow0 + local). */
 __global__ void k_generate(Mat M, u64 seed, long long grow0) {
-	const int WT = M.ns * 8;
+	const int WT = M.ns * SW;
 	long long total = M.m * WT;
 	for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
 	     t += (long long)gridDim.x * blockDim.x) {
@@ -396,19 +402,19 @@ k_select(Mat M, u64 *__restrict__ pc, int w, u64 colmask, SolverState *st, Panel
  * k_apply: per strip s >= s0: E_c = XOR_{l in TB[c]} Sel_l for every pivot column
  * c, stored (a) at matrix row r + rank(c) and (b) in ebuf[s][c] (zero rows for
  * free columns) for the sweep's TMA load; displaced rows go to the vacated
- * positions.  256 threads = 64 rows x 4 x 16 B.
- * `selsrc` != nullptr: selected rows come from a gathered buffer [ns][64][64 B]
- * (multi-GPU, after the pivot-row exchange) instead of the local matrix.
+ * positions.  512 threads = 64 rows x 8 x 16 B.
  * ---------------------------------------------------------------------- */
-__global__ void __launch_bounds__(256)
+#define APPLY_THREADS (64 * SQ)
+
+__global__ void __launch_bounds__(APPLY_THREADS)
 k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s0) {
-	__shared__ uint4 Sel[64][4];
-	__shared__ uint4 Dis[64][4];
+	__shared__ uint4 Sel[64][SQ];
+	__shared__ uint4 Dis[64][SQ];
 	__shared__ u64 sTB[64];
 	__shared__ int ssel[64], ssrc[64], sdst[64];
 	const int k = pd->k;
 	if (k == 0) return;
-	const int tid = threadIdx.x, rr = tid >> 2, ch = tid & 3;
+	const int tid = threadIdx.x, rr = tid / SQ, ch = tid % SQ;
 	const long long r = pd->r;
 	const int nmove = pd->nmove;
 	const u64 pm = pd->pm;
@@ -425,8 +431,8 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
 	for (int s = s0 + blockIdx.x; s < M.ns; s += gridDim.x) {
 		const long long sb = (long long)s * M.mp;
 		uint4 z = make_uint4(0, 0, 0, 0);
-		Sel[rr][ch] = (rr < k) ? mb[(sb + ssel[rr]) * 4 + ch] : z;
-		if (rr < nmove) Dis[rr][ch] = mb[(sb + ssrc[rr]) * 4 + ch];
+		Sel[rr][ch] = (rr < k) ? mb[(sb + ssel[rr]) * SQ + ch] : z;
+		if (rr < nmove) Dis[rr][ch] = mb[(sb + ssrc[rr]) * SQ + ch];
 		__syncthreads();
 		uint4 acc = z;
 		u64 t = sTB[rr];
@@ -436,9 +442,9 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
 			uint4 v = Sel[l][ch];
 			acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
 		}
-		ebuf[(long long)s * 256 + rr * 4 + ch] = acc;
-		if (ispiv) mb[(sb + erow) * 4 + ch] = acc;
-		if (rr < nmove) mb[(sb + sdst[rr]) * 4 + ch] = Dis[rr][ch];
+		ebuf[(long long)s * (64 * SQ) + rr * SQ + ch] = acc;
+		if (ispiv) mb[(sb + erow) * SQ + ch] = acc;
+		if (rr < nmove) mb[(sb + sdst[rr]) * SQ + ch] = Dis[rr][ch];
 		__syncthreads();
 	}
 }
@@ -446,35 +452,36 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
 /* ------------------------------------------------------------------------
  * k_sweep: the HBM-bound row-XOR sweep.
  *   rows [r1, m) x strips [s0, ns):  piece ^= XOR_g T_g[field g of (pc_cur[row] & pm)]
- * Persistent grid (1 CTA of 1024 threads per SM); work units of 1024 rows x one
- * strip are dealt out contiguously in strip-major order so a CTA rebuilds its
- * tables only when it crosses into a new strip.
+ * Persistent grid (1 CTA of 1024 threads per SM).  A work unit is 512 rows x one
+ * strip (128 B per row, 64 KiB contiguous); units are dealt out contiguously in
+ * strip-major order so a CTA rebuilds its tables only when it enters a new strip.
  *
  * Four-Russians tables, laid out for conflict-free 128-bit lookups.  A lookup
- * wavefront is a quarter-warp: 2 rows x 4 chunks of 16 B.  With plain 64-byte
- * entries the two rows collide whenever their indices have equal parity (ncu,
- * profiles/r01a: 33% of all shared wavefronts were such replays and the l1tex
- * data pipe, not HBM, was the limiter).  Here every entry lives in a 128-byte
- * line holding the SAME 64 bytes twice; the even row of the pair reads the low
- * half, the odd row the high half, so the 8 threads always cover all 32 banks.
- * The duplicated storage is paid for by splitting the 64 panel columns into
- * eight 7-bit fields (128 lines each) plus one 8-bit field (256 lines):
- * 9 lookups per 16 B instead of 8, all single-wavefront.
+ * wavefront is a quarter-warp (8 threads x 16 B).  In the first version (64-byte
+ * strips and entries) it held 2 rows x 4 chunks and the two rows collided
+ * whenever their indices had equal parity: ncu (profiles/r01a) showed 33% of all
+ * shared wavefronts were such replays and the l1tex data pipe, not HBM, was the
+ * limiter.  Now a strip piece and a table entry are both one 128-byte line and
+ * the 8 threads of a quarter-warp are the 8 chunks of ONE row: they read one
+ * whole line, all 32 banks, never a replay.  128-byte lines cost capacity, so
+ * the 64 panel columns are split into eight 7-bit fields (128 lines each) plus
+ * one 8-bit field (256 lines): 9 lookups per 16 B, all single-wavefront.
  *
- * Shared memory: TD[1280 lines][2 halves][4] uint4 (160 KiB) | P[224][4] partial
- * tables (14 KiB) | E[64][4] (4 KiB, filled by cp.async.bulk + mbarrier) | mbarrier.
+ * Shared memory: TD[1280 lines][8] uint4 = 160 KiB + the mbarrier.  The build
+ * scratch (the E tile filled by cp.async.bulk + mbarrier, partial tables P) and
+ * the fused pivot search's scratch alias table space.
  * The CTA that updates the strip holding word w+1 also emits the dense copy of
  * that word column (pc_next) for the next panel's pivot search.
  * ---------------------------------------------------------------------- */
 #define SWEEP_THREADS 1024
 #define SWEEP_U 4
-#define SWEEP_RU (SWEEP_THREADS / 4 * SWEEP_U) /* rows per unit */
+#define SWEEP_RU (SWEEP_THREADS / SQ * SWEEP_U) /* rows per unit */
 #define SWEEP_LINES (8 * 128 + 256)
 #define SWEEP_PARTS (8 * 24 + 32)
-/* 160 KiB of tables + the mbarrier.  The build scratch (E tile, partial tables) and
- * the fused pivot search's scratch alias table space, so the whole CTA stays under
- * the 164 KiB shared-memory carve-out and the SM keeps 92 KiB of L1 for the
- * streaming loads in flight (a 182 KiB layout measured 20% slower at 228 KiB carve-out). */
+#define EBUF_Q (64 * SQ) /* uint4 per strip in ebuf */
+/* 160 KiB of tables + the mbarrier: the whole CTA stays under the 164 KiB
+ * shared-memory carve-out, so the SM keeps 92 KiB of L1 for the streaming loads
+ * in flight (a 205 KiB layout measured 20% slower at the 228 KiB carve-out). */
 #define SWEEP_SMEM (SWEEP_LINES * 128 + 16)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) {
@@ -510,38 +517,42 @@ __device__ __forceinline__ void xor4(uint4 &a, const uint4 &b) {
 	a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w;
 }
 
-/* Builds TD from the pivot-row tile E (64 columns x 64 B).  E and the partial
- * tables P live inside the area of field 8 (the last 32 KiB of TD), which is
- * therefore written last, from registers.  All SWEEP_THREADS threads; ends with a
- * __syncthreads. */
+/* Builds TD from the pivot-row tile E (64 columns x 128 B).  The tile sits in the
+ * first lines of field 0 and is dead once the partial tables P exist; P sits
+ * inside field 8's area (the last 32 KiB of TD), which is therefore written last,
+ * from registers.  All SWEEP_THREADS threads; ends with a __syncthreads. */
 __device__ __forceinline__ void sweep_build_tables(uint4 *TD, uint4 *P, const uint4 *E, int tid) {
 	/* partial tables: field g < 8 (columns 7g..7g+6): 8 entries over its low 3
 	 * columns, 16 over its high 4; field 8 (columns 56..63): 16 + 16 */
-	if (tid < SWEEP_PARTS * 4) {
-		const int id = tid >> 2, ch = tid & 3;
-		int col0, e;
-		if (id < 192) {
-			const int g = id / 24, r = id - g * 24;
-			if (r < 8) { col0 = 7 * g; e = r; }
-			else { col0 = 7 * g + 3; e = r - 8; }
-		} else {
-			const int r = id - 192;
-			col0 = 56 + (r & 16 ? 4 : 0);
-			e = r & 15;
-		}
-		uint4 acc = make_uint4(0, 0, 0, 0);
 #pragma unroll
-		for (int b = 0; b < 4; b++)
-			if ((e >> b) & 1) xor4(acc, E[(col0 + b) * 4 + ch]);
-		P[tid] = acc;
+	for (int q = 0; q < 2; q++) {
+		const int it = tid + q * SWEEP_THREADS;
+		if (it < SWEEP_PARTS * 8) {
+			const int id = it >> 3, c8 = it & 7;
+			int col0, e;
+			if (id < 192) {
+				const int g = id / 24, r = id - g * 24;
+				if (r < 8) { col0 = 7 * g; e = r; }
+				else { col0 = 7 * g + 3; e = r - 8; }
+			} else {
+				const int r = id - 192;
+				col0 = 56 + (r & 16 ? 4 : 0);
+				e = r & 15;
+			}
+			uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll
+			for (int b = 0; b < 4; b++)
+				if ((e >> b) & 1) xor4(acc, E[(col0 + b) * 8 + c8]);
+			P[it] = acc;
+		}
 	}
 	__syncthreads();
-	/* fields 0..7, both halves of each line: item = (line, half, chunk) */
+	/* fields 0..7: item = (line, chunk of the 128-byte line) */
 	for (int it = tid; it < 1024 * 8; it += SWEEP_THREADS) {
-		const int L = it >> 3, ch = it & 3;
+		const int L = it >> 3, c8 = it & 7;
 		const int g = L >> 7, e = L & 127;
-		uint4 a = P[(g * 24 + (e & 7)) * 4 + ch];
-		xor4(a, P[(g * 24 + 8 + (e >> 3)) * 4 + ch]);
+		uint4 a = P[(g * 24 + (e & 7)) * 8 + c8];
+		xor4(a, P[(g * 24 + 8 + (e >> 3)) * 8 + c8]);
 		TD[it] = a;
 	}
 	/* field 8 overwrites the scratch: values to registers, barrier, then store */
@@ -549,9 +560,9 @@ __device__ __forceinline__ void sweep_build_tables(uint4 *TD, uint4 *P, const ui
 #pragma unroll
 	for (int q = 0; q < 2; q++) {
 		const int it = tid + q * SWEEP_THREADS; /* 256 lines x 8 */
-		const int e = it >> 3, ch = it & 3;
-		f8[q] = P[(192 + (e & 15)) * 4 + ch];
-		xor4(f8[q], P[(208 + (e >> 4)) * 4 + ch]);
+		const int e = it >> 3, c8 = it & 7;
+		f8[q] = P[(192 + (e & 15)) * 8 + c8];
+		xor4(f8[q], P[(208 + (e >> 4)) * 8 + c8]);
 	}
 	__syncthreads();
 #pragma unroll
@@ -560,7 +571,8 @@ __device__ __forceinline__ void sweep_build_tables(uint4 *TD, uint4 *P, const ui
 }
 
 static_assert(sizeof(SelectSmem) <= 1024 * 128, "pivot-search scratch must fit inside the tables of fields 0..7");
-static_assert((64 * 4 + SWEEP_PARTS * 4) * 16 <= 256 * 128, "build scratch must fit inside field 8's lines");
+static_assert(SWEEP_PARTS * 8 * 16 <= 256 * 128, "partial tables must fit inside field 8's lines");
+static_assert(EBUF_Q * 16 <= 128 * 128, "the E tile must fit inside field 0's lines");
 #define SWEEP_SEL_PAD 4 /* units CTA 0 is spared to make room for the fused pivot search */
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
@@ -569,8 +581,8 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
         PanelDesc *pd_next, SolverState *st, long long *hist_r, u64 *hist_pm, u64 colmask_next) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint4 *TD = reinterpret_cast<uint4 *>(smem_raw);
-	uint4 *E = TD + 1024 * 8;      /* build scratch inside field 8's lines */
-	uint4 *P = E + 64 * 4;
+	uint4 *E = TD;            /* build scratch: the E tile (8 KiB), inside field 0 ... */
+	uint4 *P = TD + 1024 * 8; /* ... and the partial tables (28 KiB), inside field 8 */
 	u64 *bar = reinterpret_cast<u64 *>(TD + SWEEP_LINES * 8);
 	/* scratch of the fused pivot search of panel w+1 (pd_next != nullptr): over the tables */
 	SelectSmem &S = *reinterpret_cast<SelectSmem *>(smem_raw);
@@ -581,7 +593,7 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 	const long long m = M.m;
 	if (r1 >= m) return;
 	const int wn = w + 1; /* next panel word (or the b word): always exists */
-	const int snext = wn >> 3;
+	const int snext = wn >> SW_SHIFT;
 	if (k == 0) {
 		/* nothing to eliminate: only hand the next word column to k_select */
 		for (long long i = r1 + blockIdx.x * (long long)SWEEP_THREADS + tid; i < m;
@@ -593,8 +605,8 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 	const long long rows = m - r1;
 	const long long nchunks = (rows + SWEEP_RU - 1) / SWEEP_RU;
 	const long long units = (long long)(M.ns - s0) * nchunks;
-	/* unit 0 = (strip of word w+1, first 1024 active rows) carries the fused pivot
-	 * search: its CTA gets SWEEP_SEL_PAD fewer units */
+	/* unit 0 = (strip holding word w+1, first SWEEP_RU active rows) carries the fused
+	 * pivot search: its CTA gets SWEEP_SEL_PAD fewer units */
 	const long long vpad = pd_next ? max(0LL, min((long long)SWEEP_SEL_PAD, units / gridDim.x - 1)) : 0;
 	const long long vunits = units + vpad;
 	const long long u0 = max(0LL, vunits * blockIdx.x / gridDim.x - vpad);
@@ -607,11 +619,10 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 	__syncthreads();
 	unsigned phase = 0;
 	int cur = -1;
-	const int ch = tid & 3, rl = tid >> 2;
-	const int nch = (wn & 7) >> 1; /* chunk holding word wn inside its strip */
+	const int ch = tid & 7, rl = tid >> 3;   /* chunk of the 128-byte piece, row in the pass */
+	const int nch = (wn & (SW - 1)) >> 1;    /* chunk holding word wn inside its strip */
 	uint4 *mb = reinterpret_cast<uint4 *>(M.base);
-	/* this thread's half of every line: rows alternate halves inside a quarter-warp */
-	const unsigned char *Tb = reinterpret_cast<const unsigned char *>(TD + (rl & 1) * 4 + ch);
+	const unsigned char *Tb = reinterpret_cast<const unsigned char *>(TD + ch);
 
 	for (long long u = u0; u < u1; ++u) {
 		const int s = s0 + (int)(u / nchunks);
@@ -619,8 +630,8 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 		if (s != cur) {
 			__syncthreads(); /* everyone is done with the previous tables */
 			if (tid == 0) {
-				mbar_expect_tx(bar, 4096);
-				tma_bulk_g2s(E, ebuf + (long long)s * 256, 4096, bar);
+				mbar_expect_tx(bar, EBUF_Q * 16);
+				tma_bulk_g2s(E, ebuf + (long long)s * EBUF_Q, EBUF_Q * 16, bar);
 			}
 			mbar_wait(bar, phase);
 			phase ^= 1;
@@ -629,20 +640,20 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 		}
 		const long long row0 = r1 + chunk * SWEEP_RU + rl;
 		const bool force = (s == snext);
-		uint4 *p = mb + ((long long)s * M.mp + row0) * 4 + ch;
+		uint4 *p = mb + ((long long)s * M.mp + row0) * SQ + ch;
 		u64 cf[SWEEP_U];
 		uint4 d[SWEEP_U];
 		bool act[SWEEP_U];
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {
-			long long row = row0 + (SWEEP_THREADS / 4) * q;
+			long long row = row0 + (SWEEP_THREADS / 8) * q;
 			cf[q] = (row < m) ? (__ldg(pc_cur + row) & pm) : 0;
 		}
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {
-			long long row = row0 + (SWEEP_THREADS / 4) * q;
+			long long row = row0 + (SWEEP_THREADS / 8) * q;
 			act[q] = (row < m) && (cf[q] != 0 || force);
-			if (act[q]) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / 4) * q * 4);
+			if (act[q]) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / 8) * q * SQ);
 		}
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {
@@ -662,14 +673,14 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 			xor4(v, TLOOK(7 * 16384 + ((hi >> 10) & 0x3F80u)));
 			xor4(v, TLOOK(8 * 16384 + ((hi >> 17) & 0x7F80u)));
 #undef TLOOK
-			__stcg(p + (long long)(SWEEP_THREADS / 4) * q * 4, v);
+			__stcg(p + (long long)(SWEEP_THREADS / 8) * q * SQ, v);
 			if (force && ch == nch) {
-				long long row = row0 + (SWEEP_THREADS / 4) * q;
+				long long row = row0 + (SWEEP_THREADS / 8) * q;
 				pc_next[row] = (wn & 1) ? (((u64)v.w << 32) | v.z) : (((u64)v.y << 32) | v.x);
 			}
 		}
 		if (pd_next && u == 0) {
-			/* This CTA just produced panel word w+1 of the first 1024 active rows.
+			/* This CTA just produced panel word w+1 of the first SWEEP_RU active rows.
 			 * Search them for the next panel's pivots while the other SMs keep
 			 * sweeping; a full set (the usual case on dense systems) or an exhausted
 			 * row range makes the description final and turns k_select into a no-op.
@@ -717,7 +728,7 @@ k_backsub(Mat M, const long long *__restrict__ hist_r, const u64 *__restrict__ h
 	extern __shared__ u64 xs[];
 	__shared__ unsigned long long newbits;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int WT = M.ns * 8;
+	const int WT = M.ns * SW;
 	for (int w = tid; w < WT; w += blockDim.x) xs[w] = 0;
 	__syncthreads();
 	if (tid == 0) {
@@ -729,20 +740,20 @@ k_backsub(Mat M, const long long *__restrict__ hist_r, const u64 *__restrict__ h
 		newbits = 0;
 	}
 	__syncthreads();
-	const int wl = lane & 7, so = lane >> 3;
+	const int wl = lane & (SW - 1), so = lane >> SW_SHIFT;
 	for (int p = M.nw - 1; p >= 0; --p) {
 		const u64 pm = hist_pm[p];
 		if (!pm) continue;
 		const int k = __popcll(pm);
 		const long long r = hist_r[p];
 		for (int j = warp; j < k; j += 32) {
-			const u64 *rowp = M.base + (r + j) * 8 + wl;
+			const u64 *rowp = M.base + (r + j) * SW + wl;
 			u64 acc = 0;
-			int s = (p >> 3) + so;
+			int s = (p >> SW_SHIFT) + so;
 #pragma unroll 4
-			for (; s < M.ns; s += 4) {
-				int wd = s * 8 + wl;
-				u64 a = rowp[(long long)s * M.mp * 8];
+			for (; s < M.ns; s += 32 / SW) {
+				int wd = s * SW + wl;
+				u64 a = rowp[(long long)s * M.mp * SW];
 				if (wd >= p) acc ^= a & xs[wd];
 			}
 			int par = __popcll(acc) & 1;

@@ -61,7 +61,7 @@ typedef struct {
 	double ms_forward;
 	double ms_backward;
 	double ms_sweep;        /* sum of k_sweep durations (profile mode only, else 0) */
-	double sweep_bytes;     /* algorithmic bytes of all sweeps: sum 2 * rows * 64 B * strips */
+	double sweep_bytes;     /* algorithmic bytes of all sweeps: sum 2 * rows * 128 B * strips */
 	double exchange_bytes;  /* multi-GPU: bytes this rank contributed to collectives */
 	int64_t sweep_launches; /* sweeps that had work (k > 0 and active rows) */
 	int64_t kernel_launches; /* all kernels launched by the elimination */

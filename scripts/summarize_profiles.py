@@ -89,15 +89,15 @@ def scale(name):
 rd = [fnum(x) * scale("dram__bytes_read.sum") for x in vals["dram__bytes_read.sum"]]
 wr = [fnum(x) * scale("dram__bytes_write.sum") for x in vals["dram__bytes_write.sum"]]
 nw = (n + 63) // 64
-ns = (nw + 1 + 7) // 8
+ns = (nw + 1 + 15) // 16
 alg = []
 for j in range(len(data)):
     w = first_panel + j
     r1 = 64 * (w + 1)
-    alg.append(2.0 * (n - r1) * 64.0 * (ns - ((w + 1) >> 3)))
+    alg.append(2.0 * (n - r1) * 128.0 * (ns - ((w + 1) >> 4)))
 ratio = sum(rd[j] + wr[j] for j in range(len(data))) / sum(alg)
 md += ["", f"DRAM traffic per launch (read+write): {[round((rd[j] + wr[j]) / 1e9, 3) for j in range(len(data))]} GB; "
-           f"algorithmic bytes of the same launches (2 * rows * 64 B * strips): {[round(a / 1e9, 3) for a in alg]} GB; "
+           f"algorithmic bytes of the same launches (2 * rows * 128 B * strips): {[round(a / 1e9, 3) for a in alg]} GB; "
            f"traffic / algorithmic = {ratio:.3f}"]
 wf = [fnum(x) for x in vals["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]]
 bc = [fnum(x) for x in vals["l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]]
