@@ -18,10 +18,13 @@
  *
  *   per panel (word column w):
  *     k_select  one CTA: XOR-basis insertion over the dense panel-column array
- *               pc[] (warp ballot picks the next pivot row, warp shuffle
- *               broadcasts its 64-bit pivot word); yields <= 64 pivot rows, the
- *               pivot-column mask (= the panel's column rank profile) and the
- *               64x64 transform TB that turns the selected rows into RREF.
+ *               pc[] (warp ballots compact the rows that survive reduction, one
+ *               warp inserts them into a register-resident basis with warp-wide
+ *               REDUX.XOR); yields <= 64 pivot rows, the pivot-column mask (= the
+ *               panel's column rank profile) and the 64x64 transform TB that
+ *               turns the selected rows into RREF.  Usually a no-op: k_sweep of
+ *               the previous panel already ran this search on the first 512
+ *               active rows while the other SMs kept sweeping.
  *     k_apply   per strip: E = TB * Sel (reduced pivot rows), stores them at rows
  *               r..r+k-1 (physical swap with the displaced rows) and into the
  *               L2-resident staging tile ebuf[s] (64 x 128 B, indexed by column).

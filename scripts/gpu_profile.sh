@@ -9,11 +9,17 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 nproc >> gpurun_out/smi_$R.txt
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_gpu_$R.txt
 timeout 900 python bench.py --steps 3 --warmup 3 2> gpurun_out/bench_$R.err | tee gpurun_out/bench_$R.json
-# launch list of one bench step (skip the warm-up step's launches)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 6200 -c 6300 --csv \
-    --log-file gpurun_out/launches_$R.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu \
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>> gpurun_out/bench_$R.err | tee gpurun_out/bench_reference_$R.json
+# launch list of one bench step: the first solve of `bench.py --steps 1 --warmup 0`
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6290 --csv \
+    --log-file gpurun_out/launches_$R.csv python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu \
     > gpurun_out/bench_under_ncu_$R.log 2>&1
-# full capture of three mid-size sweeps
+# full capture of three early (largest) sweeps
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 20 -c 3 \
     -o gpurun_out/sweep_$R python scripts/dev_bench.py 131072 0 1 > gpurun_out/ncu_full_$R.log 2>&1
+# one-GPU run of the multi-GPU size (denominator of the 8-GPU speed-up)
+if [ "${2:-}" = "big" ]; then
+  timeout 600 python bench.py --size 524288 --steps 1 --warmup 1 --no-e2e --no-cpu 2>> gpurun_out/bench_$R.err \
+      | tee gpurun_out/bench_1gpu_524288_$R.json
+fi
 ls -la gpurun_out
