@@ -57,8 +57,11 @@ def _assert_same(got, want, mode):
         assert np.array_equal(got.basis, want.basis)
 
 
+# includes the layout's edges: n = 960 / 1024 (b word last of a strip / first of the next),
+# n = 1984 / 2048 (b word inside / just past a 32-word super-panel of the back-substitution)
 SHAPES = [(1, 1), (4, 4), (5, 3), (3, 7), (64, 64), (65, 64), (64, 65), (130, 127), (200, 128),
-          (128, 200), (300, 257), (1000, 513), (1500, 1024), (2100, 2050), (1025, 3000)]
+          (128, 200), (300, 257), (1000, 513), (965, 960), (1500, 1024), (1990, 1984), (2050, 2048),
+          (2100, 2050), (1025, 3000)]
 
 
 @pytest.mark.parametrize("m,n", SHAPES)
