@@ -307,7 +307,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "config": {"workload": f"dense random {n}x{n} GF(2) echelonize + solve (BASELINE.json configs[{3 if n == 131072 else 4 if n == 524288 else '-'}])",
                        "n": n, "seed": seed, "rank": int(res.rank), "panel_bits": 64,
                        "l2": "inputs larger than L2 (matrix %.1f GB, regenerated every step)" % (n * n / 8 / 1e9),
-                       "sharding": "single GPU" if world == 1 else f"row blocks over {world} GPUs, NCCL pivot-row exchange"},
+                       "sharding": "single GPU" if world == 1 else f"row blocks over {world} GPUs, pivot-row exchange over NVLink peer memory"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "residual_bad_rows": bad,
         }

@@ -14,8 +14,9 @@
  *                     peer's exchange block, then signals flag A (release.sys);
  *   k_elect           waits for all peers' flag A (acquire.sys), then every shard
  *                     runs the same deterministic election over the G*64
- *                     candidates (priority rotates with w so rows deplete
- *                     evenly): the elected rows' pivot columns are the panel's
+ *                     candidates (taken round-robin over the shards so rows deplete
+ *                     evenly and the pull is spread over all links): the elected
+ *                     rows' pivot columns are the panel's
  *                     GLOBAL column rank profile -- what _mzd_pluq reports in Q
  *                     (reference _internal.c:433) -- because the
  *                     union of the local bases spans the global active row space;
@@ -153,14 +154,20 @@ k_elect(const XchBlock *__restrict__ xch, int G, int me, int w, u64 colmask, Sol
 	W.B0 = W.B1 = W.T0 = W.T1 = 0;
 	W.pm = 0;
 	W.nsel = 0;
-	for (int jj = 0; jj < G && W.pm != colmask; jj++) {
-		const int src = (w + jj) % G;
-		const u64 *cb = xch->cand[src];
-		const int cnt = (int)cb[0];
-		/* lanes fetch 32 candidates at a time; each is then broadcast and inserted */
-		for (int q0 = 0; q0 < cnt && W.pm != colmask; q0 += 32) {
-			const u64 mine = (q0 + lane < cnt) ? cb[1 + q0 + lane] : 0;
-			const int nq = min(32, cnt - q0);
+	/* Candidates are taken round-robin, ceil(64/G) at a time, starting with shard
+	 * w mod G: on a dense system every panel then elects ~64/G rows from EVERY shard,
+	 * so the shards deplete evenly and the pivot-row pull of k_apply_pull is spread
+	 * over all NVLink ports instead of draining one owner.  Any order gives the same
+	 * pivot columns; this one is the same on every shard. */
+	const int per = (64 + G - 1) / G;
+	for (int q0 = 0; q0 < 64 && W.pm != colmask; q0 += per) {
+		for (int jj = 0; jj < G && W.pm != colmask; jj++) {
+			const int src = (w + jj) % G;
+			const u64 *cb = xch->cand[src];
+			const int cnt = (int)cb[0];
+			const int nq = min(per, cnt - q0); /* per <= 32: one candidate per lane */
+			if (nq <= 0) continue;
+			const u64 mine = (lane < nq) ? cb[1 + q0 + lane] : 0;
 			for (int j = 0; j < nq && W.pm != colmask; j++)
 				wb_insert(W, sel, shfl64(mine, j), 0, src * 64 + q0 + j, lane);
 		}
