@@ -155,22 +155,35 @@ static uint64_t *stage_reserve(size_t bytes) {
 /* Equation int -> one matrix row.  Bit 0 is the constant term (returned), bit k
  * (1..cols) is the coefficient of unknown k-1 and lands at row bit k-1; higher
  * bits are dropped and the sign is ignored (digits are the magnitude), exactly
- * what the reference's bit walk does (:41-59, :411-425).  `row` must be zeroed. */
+ * what the reference's bit walk does (:41-59, :411-425).  Streams the 30-bit
+ * digits through a 128-bit accumulator and writes every word of the row exactly
+ * once (the staging buffer needs no clearing). */
 static inline int pack_equation(PyObject *eq, uint64_t *row, int64_t nw, int64_t cols) {
 	const Py_ssize_t nd = LONG_NDIGITS(eq);
-	if (nd == 0) return 0;
+	if (nd == 0) {
+		memset(row, 0, (size_t)nw * 8);
+		return 0;
+	}
 	const digit *d = LONG_DIGITS(eq);
 	const int cbit = (int)(d[0] & 1);
-	row[0] = (uint64_t)d[0] >> 1;
-	int64_t pos = PyLong_SHIFT - 1; /* row bit where digit i starts */
-	for (Py_ssize_t i = 1; i < nd; i++, pos += PyLong_SHIFT) {
-		const int64_t w = pos >> 6;
-		if (w >= nw) break;
-		const int off = (int)(pos & 63);
-		const uint64_t v = d[i];
-		row[w] |= v << off;
-		if (off + PyLong_SHIFT > 64 && w + 1 < nw) row[w + 1] |= v >> (64 - off);
+	unsigned __int128 acc = (unsigned __int128)(d[0] >> 1);
+	int nbits = PyLong_SHIFT - 1; /* valid bits waiting in acc */
+	Py_ssize_t i = 1;
+	int64_t w = 0;
+	for (; w < nw; w++) {
+		while (nbits < 64 && i < nd) {
+			acc |= (unsigned __int128)d[i++] << nbits;
+			nbits += PyLong_SHIFT;
+		}
+		row[w] = (uint64_t)acc;
+		acc >>= 64;
+		nbits = nbits > 64 ? nbits - 64 : 0;
+		if (i >= nd && nbits == 0) {
+			w++;
+			break;
+		}
 	}
+	if (w < nw) memset(row + w, 0, (size_t)(nw - w) * 8);
 	if (cols & 63) row[nw - 1] &= (1ULL << (cols & 63)) - 1;
 	return cbit;
 }
@@ -484,7 +497,7 @@ static PyObject *m4ri_solve(PyObject *self, PyObject *const *args, Py_ssize_t na
 	uint64_t *A = stage_reserve(((size_t)rows * nw + bw) * 8);
 	if (!A) goto out;
 	uint64_t *b = A + (size_t)rows * nw;
-	memset(A, 0, ((size_t)rows * nw + bw) * 8);
+	memset(b, 0, (size_t)bw * 8); /* the packer writes every word of A itself */
 	int any_b = 0;
 	for (Py_ssize_t r = 0; r < rows; r++) {
 		if (pack_equation(PyList_GET_ITEM(eqs, r), A + (size_t)r * nw, nw, cols)) {
