@@ -302,6 +302,7 @@ __device__ __forceinline__ void select_scan(SelectSmem &S, const u64 *__restrict
 			for (int q = 0; q < total && W.pm != colmask; q++)
 				wb_insert(W, S.sel, S.qv[q], S.qtv[q], S.qrow[q], lane);
 			wb_store(W, S.B, S.TB, lane);
+			__syncwarp(); /* every lane has read S.nsel / S.pm before lane 0 replaces them */
 			if (lane == 0) {
 				S.pm = W.pm;
 				S.nsel = W.nsel;
