@@ -33,6 +33,19 @@ def test_library_exports_every_declared_symbol():
     assert lib.gf2b200_abi_version() == 1
 
 
+def test_ctypes_mirrors_match_header_structs():
+    """The ctypes Structures in _shim.py must list the header's struct fields in order."""
+    header = (ROOT / "include" / "gf2b200.h").read_text()
+
+    def fields(struct_name):
+        body = re.search(r"typedef struct \{((?:(?!typedef struct).)*?)\} " + struct_name + ";", header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        return [re.split(r"[\s\*]+", decl.strip())[-1] for decl in body.split(";") if decl.strip()]
+
+    assert fields("gf2b200_result") == [n for n, _ in _shim.CResult._fields_]
+    assert fields("gf2b200_stats") == [n for n, _ in _shim.CStats._fields_]
+
+
 def test_extension_surface_matches_reference_names():
     # gf2bv/__init__.py:8-16 imports these seven; _internal.c:829-831 adds the types
     for name in ("AffineSpace", "eqs_to_sage_mat_helper", "m4ri_solve", "mul_bit_quad", "to_bits",
