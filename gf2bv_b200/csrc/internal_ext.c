@@ -188,6 +188,76 @@ static inline int pack_equation(PyObject *eq, uint64_t *row, int64_t nw, int64_t
 	return cbit;
 }
 
+/* All equations -> A (rows x nw words) and b (rows bits).  Large systems are packed
+ * by several threads WITHOUT the GIL: the caller's list items are pinned by strong
+ * references for the duration (ints are immutable, so their digits can be read from
+ * any thread); rows are split in blocks of 64 so no two threads share a word of b.
+ * The reference packs one bit at a time under the GIL (_internal.c:403-426). */
+typedef struct {
+	PyObject **items;
+	uint64_t *A, *b;
+	int64_t nw, cols;
+	Py_ssize_t r0, r1;
+	int any_b;
+} pack_job;
+
+static void *pack_worker(void *arg) {
+	pack_job *j = (pack_job *)arg;
+	int any = 0;
+	for (Py_ssize_t r = j->r0; r < j->r1; r++) {
+		if ((r & 63) == 0 || r == j->r0) j->b[r >> 6] = 0;
+		if (pack_equation(j->items[r], j->A + (size_t)r * j->nw, j->nw, j->cols)) {
+			j->b[r >> 6] |= 1ULL << (r & 63);
+			any = 1;
+		}
+	}
+	j->any_b = any;
+	return NULL;
+}
+
+#define PACK_MAX_THREADS 8
+#define PACK_MIN_WORDS_PER_THREAD (1 << 20)
+
+/* GIL held on entry and exit; items are already type-checked.  Returns any_b, or -1 on error. */
+static int pack_all(PyObject *list, Py_ssize_t rows, uint64_t *A, uint64_t *b, int64_t nw, int64_t cols) {
+	PyObject **items = ((PyListObject *)list)->ob_item;
+	int nthreads = (int)(((int64_t)rows * nw) / PACK_MIN_WORDS_PER_THREAD);
+	if (nthreads > PACK_MAX_THREADS) nthreads = PACK_MAX_THREADS;
+	if (nthreads < 2) {
+		pack_job j = {items, A, b, nw, cols, 0, rows, 0};
+		pack_worker(&j);
+		return j.any_b;
+	}
+	/* the list may be mutated by other Python threads once the GIL is released:
+	 * work on a private, reference-holding copy of the item pointers */
+	PyObject **held = (PyObject **)malloc((size_t)rows * sizeof(PyObject *));
+	if (!held) {
+		PyErr_NoMemory();
+		return -1;
+	}
+	for (Py_ssize_t r = 0; r < rows; r++) held[r] = Py_NewRef(items[r]);
+	pack_job jobs[PACK_MAX_THREADS];
+	pthread_t tids[PACK_MAX_THREADS];
+	int started[PACK_MAX_THREADS];
+	const Py_ssize_t blocks = (rows + 63) / 64;
+	Py_BEGIN_ALLOW_THREADS
+	for (int t = 0; t < nthreads; t++) {
+		Py_ssize_t r0 = blocks * t / nthreads * 64, r1 = blocks * (t + 1) / nthreads * 64;
+		if (r1 > rows) r1 = rows;
+		jobs[t] = (pack_job){held, A, b, nw, cols, r0, r1, 0};
+		started[t] = (t + 1 < nthreads) && pthread_create(&tids[t], NULL, pack_worker, &jobs[t]) == 0;
+		if (!started[t]) pack_worker(&jobs[t]); /* the last block, or thread creation failed */
+	}
+	for (int t = 0; t < nthreads; t++)
+		if (started[t]) pthread_join(tids[t], NULL);
+	Py_END_ALLOW_THREADS
+	int any = 0;
+	for (int t = 0; t < nthreads; t++) any |= jobs[t].any_b;
+	for (Py_ssize_t r = 0; r < rows; r++) Py_DECREF(held[r]);
+	free(held);
+	return any;
+}
+
 /* packed little-endian words -> Python int (bit c of the int = bit c of the row;
  * replaces mzd_vector_to_pylong, reference :32-39) */
 static PyObject *words_to_pylong(const uint64_t *w, int64_t nw) {
@@ -496,15 +566,9 @@ static PyObject *m4ri_solve(PyObject *self, PyObject *const *args, Py_ssize_t na
 	if (ctx_ready()) goto out;
 	uint64_t *A = stage_reserve(((size_t)rows * nw + bw) * 8);
 	if (!A) goto out;
-	uint64_t *b = A + (size_t)rows * nw;
-	memset(b, 0, (size_t)bw * 8); /* the packer writes every word of A itself */
-	int any_b = 0;
-	for (Py_ssize_t r = 0; r < rows; r++) {
-		if (pack_equation(PyList_GET_ITEM(eqs, r), A + (size_t)r * nw, nw, cols)) {
-			b[r >> 6] |= 1ULL << (r & 63);
-			any_b = 1;
-		}
-	}
+	uint64_t *b = A + (size_t)rows * nw; /* the packer writes every word of A and b itself */
+	const int any_b = pack_all(eqs, rows, A, b, nw, cols);
+	if (any_b < 0) goto out;
 
 	gf2b200_result res;
 	int rc;
@@ -734,17 +798,19 @@ static PyObject *pack_probe(PyObject *self, PyObject *const *args, Py_ssize_t na
 		return NULL;
 	}
 	uint64_t *A = (uint64_t *)PyBytes_AS_STRING(pa), *b = (uint64_t *)PyBytes_AS_STRING(pb);
-	memset(A, 0, (size_t)rows * nw * 8);
 	memset(b, 0, (size_t)bw * 8);
 	for (Py_ssize_t r = 0; r < rows; r++) {
-		PyObject *it = PyList_GET_ITEM(args[0], r);
-		if (!PyLong_Check(it)) {
+		if (!PyLong_Check(PyList_GET_ITEM(args[0], r))) {
 			Py_DECREF(pa);
 			Py_DECREF(pb);
 			PyErr_SetString(PyExc_TypeError, "List items must be integers");
 			return NULL;
 		}
-		if (pack_equation(it, A + (size_t)r * nw, nw, cols)) b[r >> 6] |= 1ULL << (r & 63);
+	}
+	if (pack_all(args[0], rows, A, b, nw, cols) < 0) {
+		Py_DECREF(pa);
+		Py_DECREF(pb);
+		return NULL;
 	}
 	PyObject *ret = PyTuple_Pack(2, pa, pb);
 	Py_DECREF(pa);

@@ -71,6 +71,18 @@ def test_pack_codec_matches_oracle_restatement():
         assert np.array_equal(B, wantB), cols
 
 
+def test_pack_codec_threaded_path():
+    """>= 2^21 words: rows are packed by several threads without the GIL (64-row blocks)."""
+    rnd = random.Random(2)
+    rows, cols = 70001, 3000
+    eqs = [rnd.getrandbits(rnd.choice([1, cols // 2, cols + 1, cols + 40])) * rnd.choice([1, -1]) for _ in range(rows)]
+    a, b = _internal._pack_probe(eqs, cols)
+    A = np.frombuffer(a, dtype=np.uint64).reshape(rows, -1)
+    B = np.frombuffer(b, dtype=np.uint64)
+    wantA, wantB = oracle.pack_equations(eqs, cols)
+    assert np.array_equal(A, wantA) and np.array_equal(B, wantB)
+
+
 def test_pack_codec_rejects_non_ints():
     with pytest.raises(TypeError):
         _internal._pack_probe([1, 2.0], 4)
