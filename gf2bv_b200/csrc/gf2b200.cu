@@ -9,10 +9,12 @@
  *
  * A system is a set of row shards.  Three kinds of context:
  *   single    one shard on one GPU (gf2b200_create);
- *   nccl      one shard per process/GPU, exchanges over NCCL (gf2b200_create_dist);
- *   loopback  `world` shards on ONE GPU in one process, exchanges are device
- *             copies (gf2b200_create_shards) -- same kernels and control flow as
- *             the nccl kind, so the sharded path can be parity-tested on one GPU.
+ *   nccl      one shard per process/GPU (gf2b200_create_dist): NCCL is the rendezvous
+ *             (IPC handle exchange, back-substitution slabs), the per-panel pivot
+ *             exchange is NVLink loads/stores on peer memory from our own kernels;
+ *   loopback  `world` shards on ONE GPU in one process (gf2b200_create_shards): the
+ *             peers are local pointers -- same kernels and control flow as the nccl
+ *             kind, so the sharded path can be parity-tested on one GPU.
  */
 #include "gf2b200_dist.cuh"
 
@@ -364,7 +366,6 @@ static int map_peers(gf2b200_system *sys) {
 		return GF2B200_OK;
 	}
 	Shard &h = sys->sh[0];
-	const size_t mat_bytes = (size_t)h.M.ns * (size_t)h.M.mp * SBYTES;
 	cudaIpcMemHandle_t mine;
 	CK(ctx, cudaIpcGetMemHandle(&mine, h.M.base));
 	std::vector<cudaIpcMemHandle_t> all((size_t)G);
@@ -394,7 +395,6 @@ static int map_peers(gf2b200_system *sys) {
 		/* the peer's exchange block sits behind ITS matrix: ns is global, mp is per shard */
 		pt.xch[g] = reinterpret_cast<XchBlock *>((char *)p + (size_t)h.M.ns * (size_t)pt.mp[g] * SBYTES);
 	}
-	(void)mat_bytes;
 	CK(ctx, cudaMemcpy(h.d_pt, &pt, sizeof pt, cudaMemcpyHostToDevice));
 	return GF2B200_OK;
 }

@@ -79,14 +79,17 @@ int gf2b200_device_count(void);
 
 /* One context per caller thread and device (stream, workspaces). */
 int gf2b200_create(gf2b200_ctx **out, int device);
-/* Multi-GPU context: one process per GPU; `nccl_id128` is the 128-byte ncclUniqueId
- * from gf2b200_nccl_unique_id() on rank 0, distributed by the caller. */
+/* Multi-GPU context: one process per GPU of one NVLink-connected node; `nccl_id128`
+ * is the 128-byte ncclUniqueId from gf2b200_nccl_unique_id() on rank 0, distributed
+ * by the caller.  NCCL is the rendezvous only: systems of such a context map each
+ * other's HBM with CUDA IPC and exchange pivot rows with NVLink loads/stores, so
+ * gf2b200_system_create / _destroy are collective (same order on every rank). */
 int gf2b200_nccl_unique_id(void *out_id128);
 int gf2b200_create_dist(gf2b200_ctx **out, int device, int rank, int world,
                         const void *nccl_id128);
 /* Loopback context: `world` row shards on ONE device in this process; the
  * exchanges of the sharded algorithm become device copies.  Same kernels and
- * control flow as the NCCL kind -- used to parity-test the sharded path on one
+ * control flow as the multi-process kind -- used to parity-test the sharded path on one
  * GPU.  Systems of such a context take the WHOLE matrix in system_load_*. */
 int gf2b200_create_shards(gf2b200_ctx **out, int device, int world);
 void gf2b200_destroy(gf2b200_ctx *ctx);
