@@ -478,7 +478,9 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
  * that word column (pc_next) for the next panel's pivot search.
  * ---------------------------------------------------------------------- */
 #define SWEEP_THREADS 1024
-#define SWEEP_U 4
+#ifndef SWEEP_U
+#define SWEEP_U 4 /* row pieces in flight per thread (2, 3, 6 measured slower) */
+#endif
 #define SWEEP_RU (SWEEP_THREADS / SQ * SWEEP_U) /* rows per unit */
 #define SWEEP_LINES (8 * 128 + 256)
 #define SWEEP_PARTS (8 * 24 + 32)
@@ -577,7 +579,9 @@ __device__ __forceinline__ void sweep_build_tables(uint4 *TD, uint4 *P, const ui
 static_assert(sizeof(SelectSmem) <= 1024 * 128, "pivot-search scratch must fit inside the tables of fields 0..7");
 static_assert(SWEEP_PARTS * 8 * 16 <= 256 * 128, "partial tables must fit inside field 8's lines");
 static_assert(EBUF_Q * 16 <= 128 * 128, "the E tile must fit inside field 0's lines");
+#ifndef SWEEP_SEL_PAD
 #define SWEEP_SEL_PAD 4 /* units CTA 0 is spared to make room for the fused pivot search */
+#endif
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
 k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
