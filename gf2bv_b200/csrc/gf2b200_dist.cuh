@@ -68,6 +68,7 @@ struct DistPanel {
 	int srow[64];        /* ... and its row number there */
 };
 
+#ifndef GF2_EMU
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
 	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -81,6 +82,12 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
 	return t;
 }
+#else
+/* tests/cpu_emu only: one thread runs everything, plain accesses are ordered */
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) { *(volatile unsigned *)p = v; }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) { return *(const volatile unsigned *)p; }
+__device__ __forceinline__ unsigned long long globaltimer_ns() { return (unsigned long long)(emu_now_ms() * 1e6); }
+#endif
 /* spin until *flag >= epoch (epochs only grow); gives up after ~4 s and reports a fault */
 __device__ __forceinline__ bool wait_flag(const unsigned *flag, unsigned epoch) {
 	const unsigned long long t0 = globaltimer_ns();

@@ -43,10 +43,25 @@ typedef unsigned long long u64;
 
 #define GF2_PHI 0x9E3779B97F4A7C15ULL
 
+/* Strip geometry (compile-time): GF2_STRIP_WORDS = 16 -> 128-byte strips, nine
+ * lookup tables of whole 128-byte lines; 8 -> 64-byte strips, eight tables stored
+ * as four line PAIRS (see k_sweep). */
+#ifndef GF2_STRIP_WORDS
+#define GF2_STRIP_WORDS 16
+#endif
+#if GF2_STRIP_WORDS == 16
 #define SW 16        /* 64-bit words per strip piece */
 #define SW_SHIFT 4
 #define SQ 8         /* 16-byte chunks per strip piece */
 #define SBYTES 128   /* bytes per strip piece */
+#elif GF2_STRIP_WORDS == 8
+#define SW 8
+#define SW_SHIFT 3
+#define SQ 4
+#define SBYTES 64
+#else
+#error "GF2_STRIP_WORDS must be 16 or 8"
+#endif
 
 struct Mat {
 	u64 *base;      /* strip-major storage, ns * mp * SW words */
@@ -482,14 +497,29 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
 #define SWEEP_U 4 /* row pieces in flight per thread (2, 3, 6 measured slower) */
 #endif
 #define SWEEP_RU (SWEEP_THREADS / SQ * SWEEP_U) /* rows per unit */
+#define EBUF_Q (64 * SQ) /* uint4 per strip in ebuf */
+#if SW == 16
 #define SWEEP_LINES (8 * 128 + 256)
 #define SWEEP_PARTS (8 * 24 + 32)
-#define EBUF_Q (64 * SQ) /* uint4 per strip in ebuf */
 /* 160 KiB of tables + the mbarrier: the whole CTA stays under the 164 KiB
  * shared-memory carve-out, so the SM keeps 92 KiB of L1 for the streaming loads
  * in flight (a 205 KiB layout measured 20% slower at the 228 KiB carve-out). */
 #define SWEEP_SMEM (SWEEP_LINES * 128 + 16)
+#else
+/* 64-byte strips: eight 256-entry tables of 64-byte entries stored as four line
+ * PAIRS -- line e of pair p holds T_{2p}[e] in bytes 0..63 and T_{2p+1}[e] in bytes
+ * 64..127.  A lookup wavefront (quarter-warp) is 2 rows x 4 chunks; the two rows
+ * visit the two tables of a pair in OPPOSITE order, so at every step one row reads
+ * banks 0..15 and the other banks 16..31 whatever their indices are: 8 lookups per
+ * 16 B, all single-wavefront, 128 KiB of tables.  The E tile (4 KiB) and the nibble
+ * partial tables (16.5 KiB) have their own space: 148.5 KiB, still under the
+ * 164 KiB carve-out. */
+#define SWEEP_LINES (4 * 256)
+#define SWEEP_PSTRIDE 132 /* uint4 per table in P: 32 entries x 4 chunks + 64 B skew (tables 2p / 2p+1 on opposite bank halves) */
+#define SWEEP_SMEM (SWEEP_LINES * 128 + EBUF_Q * 16 + 8 * SWEEP_PSTRIDE * 16 + 16)
+#endif
 
+#ifndef GF2_EMU
 __device__ __forceinline__ unsigned smem_u32(const void *p) {
 	return (unsigned)__cvta_generic_to_shared(p);
 }
@@ -518,11 +548,27 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigne
 	    "l"(src), "r"(bytes), "r"(smem_u32(bar))
 	    : "memory");
 }
+__device__ __forceinline__ void mbar_init_fence() {
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+#else
+/* tests/cpu_emu only (the kernels' source executed on the CPU; never in libgf2b200.so):
+ * the copy completes at once and flips the barrier's phase bit */
+__device__ __forceinline__ void mbar_init(void *bar, unsigned) { emu_mbar_init(bar); }
+__device__ __forceinline__ void mbar_init_fence() {}
+__device__ __forceinline__ void mbar_expect_tx(void *, unsigned) {}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned phase) { emu_mbar_wait(bar, phase); }
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar) {
+	memcpy(dst, src, bytes);
+	emu_mbar_complete(bar);
+}
+#endif
 
 __device__ __forceinline__ void xor4(uint4 &a, const uint4 &b) {
 	a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w;
 }
 
+#if SW == 16
 /* Builds TD from the pivot-row tile E (64 columns x 128 B).  The tile sits in the
  * first lines of field 0 and is dead once the partial tables P exist; P sits
  * inside field 8's area (the last 32 KiB of TD), which is therefore written last,
@@ -579,6 +625,37 @@ __device__ __forceinline__ void sweep_build_tables(uint4 *TD, uint4 *P, const ui
 static_assert(sizeof(SelectSmem) <= 1024 * 128, "pivot-search scratch must fit inside the tables of fields 0..7");
 static_assert(SWEEP_PARTS * 8 * 16 <= 256 * 128, "partial tables must fit inside field 8's lines");
 static_assert(EBUF_Q * 16 <= 128 * 128, "the E tile must fit inside field 0's lines");
+#else
+/* Builds the four line pairs from the pivot-row tile E (64 columns x 64 B).
+ * Step 1: per table t (columns 8t..8t+7) 16 combinations of its low 4 columns and
+ * 16 of its high 4 (one item per thread).  Step 2: entry e = lo[e & 15] ^ hi[e >> 4],
+ * written into the half-line of its table.  Ends with a __syncthreads. */
+__device__ __forceinline__ void sweep_build_tables(uint4 *TD, uint4 *P, const uint4 *E, int tid) {
+	{
+		const int t = tid >> 7, e5 = (tid >> 2) & 31, c4 = tid & 3;
+		const int col0 = 8 * t + (e5 & 16 ? 4 : 0), e = e5 & 15;
+		uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll
+		for (int b = 0; b < 4; b++)
+			if ((e >> b) & 1) xor4(acc, E[(col0 + b) * 4 + c4]);
+		P[t * SWEEP_PSTRIDE + e5 * 4 + c4] = acc;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int q = 0; q < SWEEP_LINES * 8 / SWEEP_THREADS; q++) {
+		const int it = tid + q * SWEEP_THREADS; /* (line, chunk of the 128-byte line) */
+		const int L = it >> 3, c8 = it & 7;
+		const int t = 2 * (L >> 8) + (c8 >> 2), e = L & 255, c4 = c8 & 3;
+		uint4 a = P[t * SWEEP_PSTRIDE + (e & 15) * 4 + c4];
+		xor4(a, P[t * SWEEP_PSTRIDE + (16 + (e >> 4)) * 4 + c4]);
+		TD[it] = a;
+	}
+	__syncthreads();
+}
+
+static_assert(sizeof(SelectSmem) <= SWEEP_LINES * 128, "pivot-search scratch must fit inside the tables");
+static_assert(SWEEP_THREADS == 8 * 32 * 4, "one partial-table item per thread");
+#endif
 #ifndef SWEEP_SEL_PAD
 #define SWEEP_SEL_PAD 4 /* units CTA 0 is spared to make room for the fused pivot search */
 #endif
@@ -589,9 +666,15 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
         PanelDesc *pd_next, SolverState *st, long long *hist_r, u64 *hist_pm, u64 colmask_next) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint4 *TD = reinterpret_cast<uint4 *>(smem_raw);
+#if SW == 16
 	uint4 *E = TD;            /* build scratch: the E tile (8 KiB), inside field 0 ... */
 	uint4 *P = TD + 1024 * 8; /* ... and the partial tables (28 KiB), inside field 8 */
 	u64 *bar = reinterpret_cast<u64 *>(TD + SWEEP_LINES * 8);
+#else
+	uint4 *E = TD + SWEEP_LINES * 8; /* the E tile and the partial tables follow the tables */
+	uint4 *P = E + EBUF_Q;
+	u64 *bar = reinterpret_cast<u64 *>(P + 8 * SWEEP_PSTRIDE);
+#endif
 	/* scratch of the fused pivot search of panel w+1 (pd_next != nullptr): over the tables */
 	SelectSmem &S = *reinterpret_cast<SelectSmem *>(smem_raw);
 
@@ -622,15 +705,25 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 	if (u0 >= u1) return;
 	if (tid == 0) {
 		mbar_init(bar, 1);
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		mbar_init_fence();
 	}
 	__syncthreads();
 	unsigned phase = 0;
 	int cur = -1;
-	const int ch = tid & 7, rl = tid >> 3;   /* chunk of the 128-byte piece, row in the pass */
+	const int ch = tid % SQ, rl = tid / SQ;  /* chunk of the strip piece, row in the pass */
 	const int nch = (wn & (SW - 1)) >> 1;    /* chunk holding word wn inside its strip */
 	uint4 *mb = reinterpret_cast<uint4 *>(M.base);
+#if SW == 16
 	const unsigned char *Tb = reinterpret_cast<const unsigned char *>(TD + ch);
+#else
+	/* the two rows of a quarter-warp take the tables of a pair in opposite order:
+	 * row parity h reads half h at even steps and half 1-h at odd steps, and sees
+	 * its coefficient with adjacent bytes swapped when h = 1 */
+	const int h = rl & 1;
+	const unsigned char *Tbe = reinterpret_cast<const unsigned char *>(TD + 4 * h + ch);
+	const unsigned char *Tbo = reinterpret_cast<const unsigned char *>(TD + 4 * (1 - h) + ch);
+	const unsigned bsel = h ? 0x2301u : 0x3210u;
+#endif
 
 	for (long long u = u0; u < u1; ++u) {
 		const int s = s0 + (int)(u / nchunks);
@@ -654,21 +747,22 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 		bool act[SWEEP_U];
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {
-			long long row = row0 + (SWEEP_THREADS / 8) * q;
+			long long row = row0 + (SWEEP_THREADS / SQ) * q;
 			cf[q] = (row < m) ? (__ldg(pc_cur + row) & pm) : 0;
 		}
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {
-			long long row = row0 + (SWEEP_THREADS / 8) * q;
+			long long row = row0 + (SWEEP_THREADS / SQ) * q;
 			act[q] = (row < m) && (cf[q] != 0 || force);
-			if (act[q]) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / 8) * q * SQ);
+			if (act[q]) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ);
 		}
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {
 			if (!act[q]) continue;
+			uint4 v = d[q];
+#if SW == 16
 			const unsigned lo = (unsigned)cf[q], hi = (unsigned)(cf[q] >> 32);
 			const unsigned mid = __funnelshift_r(lo, hi, 28);
-			uint4 v = d[q];
 			/* byte offset of a line = 128 * (field base + field value) */
 #define TLOOK(off) (*reinterpret_cast<const uint4 *>(Tb + (off)))
 			xor4(v, TLOOK(0 * 16384 + ((lo << 7) & 0x3F80u)));
@@ -681,9 +775,24 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 			xor4(v, TLOOK(7 * 16384 + ((hi >> 10) & 0x3F80u)));
 			xor4(v, TLOOK(8 * 16384 + ((hi >> 17) & 0x7F80u)));
 #undef TLOOK
-			__stcg(p + (long long)(SWEEP_THREADS / 8) * q * SQ, v);
+#else
+			const unsigned lo = __byte_perm((unsigned)cf[q], 0, bsel);
+			const unsigned hi = __byte_perm((unsigned)(cf[q] >> 32), 0, bsel);
+			/* byte offset of a line = 32768 * pair + 128 * (byte of the coefficient) */
+#define TLOOK(base, off) (*reinterpret_cast<const uint4 *>((base) + (off)))
+			xor4(v, TLOOK(Tbe, 0 * 32768 + ((lo << 7) & 0x7F80u)));
+			xor4(v, TLOOK(Tbo, 0 * 32768 + ((lo >> 1) & 0x7F80u)));
+			xor4(v, TLOOK(Tbe, 1 * 32768 + ((lo >> 9) & 0x7F80u)));
+			xor4(v, TLOOK(Tbo, 1 * 32768 + ((lo >> 17) & 0x7F80u)));
+			xor4(v, TLOOK(Tbe, 2 * 32768 + ((hi << 7) & 0x7F80u)));
+			xor4(v, TLOOK(Tbo, 2 * 32768 + ((hi >> 1) & 0x7F80u)));
+			xor4(v, TLOOK(Tbe, 3 * 32768 + ((hi >> 9) & 0x7F80u)));
+			xor4(v, TLOOK(Tbo, 3 * 32768 + ((hi >> 17) & 0x7F80u)));
+#undef TLOOK
+#endif
+			__stcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ, v);
 			if (force && ch == nch) {
-				long long row = row0 + (SWEEP_THREADS / 8) * q;
+				long long row = row0 + (SWEEP_THREADS / SQ) * q;
 				pc_next[row] = (wn & 1) ? (((u64)v.w << 32) | v.z) : (((u64)v.y << 32) | v.x);
 			}
 		}

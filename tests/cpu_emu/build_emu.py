@@ -1,0 +1,123 @@
+"""TEST INFRASTRUCTURE ONLY: build a CPU-executable copy of libgf2b200 from the
+CUDA sources (gf2bv_b200/csrc/*.cu, *.cuh) so the kernels' logic can be checked on
+a machine without a GPU.  See include/cuda_runtime.h for what the emulation is and
+is not.  The product (libgf2b200.so, nvcc, sm_100a) never contains any of this.
+
+    python tests/cpu_emu/build_emu.py [--strip-words 16|8] -> prints the .so path
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import re
+import subprocess
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+CSRC = ROOT / "gf2bv_b200" / "csrc"
+BUILD = HERE / "_build"
+
+
+def _split_top(s: str) -> list[str]:
+    """split on commas that are not nested in (), [], {}"""
+    out, depth, cur = [], 0, []
+    for ch in s:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(ch)
+    out.append("".join(cur).strip())
+    return out
+
+
+def rewrite_launches(src: str) -> str:
+    """kernel<<<grid, block, smem, stream>>>(args)  ->  EMU_LAUNCH(kernel, grid, block, smem, stream, args)"""
+    out = []
+    pos = 0
+    while True:
+        i = src.find("<<<", pos)
+        if i < 0:
+            out.append(src[pos:])
+            break
+        m = re.search(r"([A-Za-z_][A-Za-z_0-9]*)\s*$", src[pos:i])
+        if not m:  # "<<<" inside a comment
+            out.append(src[pos:i + 3])
+            pos = i + 3
+            continue
+        name_start = pos + m.start(1)
+        j = src.index(">>>", i)
+        cfg = _split_top(src[i + 3:j])
+        while len(cfg) < 4:
+            cfg.append("0")
+        k = j + 3
+        while src[k].isspace():
+            k += 1
+        assert src[k] == "(", "launch without an argument list"
+        depth, e = 0, k
+        while True:
+            if src[e] == "(":
+                depth += 1
+            elif src[e] == ")":
+                depth -= 1
+                if depth == 0:
+                    break
+            e += 1
+        args = src[k + 1:e].strip()
+        out.append(src[pos:name_start])
+        out.append(f"EMU_LAUNCH({m.group(1)}, {', '.join(cfg)}" + (f", {args})" if args else ")"))
+        pos = e + 1
+    return "".join(out)
+
+
+def transform(text: str) -> str:
+    text = rewrite_launches(text)
+    # dynamic shared memory: one process-wide buffer per name (CTAs run one at a time)
+    text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?", "extern ", text)
+    return text
+
+
+def build(strip_words: int = 16, force: bool = False) -> Path:
+    out_dir = BUILD / f"sw{strip_words}"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    lib = out_dir / "libgf2b200_emu.so"
+    srcs = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [
+        ROOT / "include" / "gf2b200.h", HERE / "include" / "cuda_runtime.h", HERE / "include" / "nccl.h",
+        HERE / "emu_runtime.cpp", Path(__file__)]
+    if not force and lib.exists() and all(lib.stat().st_mtime >= s.stat().st_mtime for s in srcs):
+        return lib
+    # mirror the source tree's relative layout: gf2b200.cu includes "../../include/gf2b200.h"
+    gen = out_dir / "gf2bv_b200" / "csrc"
+    gen.mkdir(parents=True, exist_ok=True)
+    for s in list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")):
+        (gen / (s.name + (".cpp" if s.suffix == ".cu" else ""))).write_text(transform(s.read_text()))
+    inc_link = out_dir / "include"
+    if not inc_link.exists():
+        os.symlink(ROOT / "include", inc_link)
+    # storage behind the kernels' `extern __shared__` arrays
+    (gen / "emu_shared.cpp").write_text(
+        "namespace gf2b200 {\n"
+        "alignas(128) unsigned char smem_raw[232 * 1024];\n"
+        "alignas(128) unsigned long long xs[232 * 1024 / 8];\n"
+        "}\n")
+    tmp = lib.with_suffix(f".tmp{os.getpid()}.so")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-w", f"-DGF2_STRIP_WORDS={strip_words}",
+           "-I", str(HERE / "include"), "-I", str(gen),
+           "-o", str(tmp), str(gen / "gf2b200.cu.cpp"), str(gen / "emu_shared.cpp"), str(HERE / "emu_runtime.cpp"),
+           "-ldl"]
+    subprocess.check_call(cmd)
+    os.replace(tmp, lib)
+    return lib
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--strip-words", type=int, default=16)
+    ap.add_argument("--force", action="store_true")
+    a = ap.parse_args()
+    print(build(a.strip_words, a.force))

@@ -1,0 +1,128 @@
+/*
+ * emu_runtime.cpp -- TEST INFRASTRUCTURE ONLY (see include/cuda_runtime.h): the
+ * fiber scheduler that runs a grid's CTAs one after another on the calling thread.
+ */
+#include <cuda_runtime.h>
+#include <sys/mman.h>
+
+namespace emu {
+
+Fiber *cur = nullptr;
+Cta cta;
+dim3 g_blockIdx, g_blockDim, g_gridDim;
+void *sched_sp = nullptr;
+
+static const size_t STACK = 64 * 1024;
+static char *stacks = nullptr;
+static size_t n_stacks = 0;
+static void (*g_thunk)(void *) = nullptr;
+static void *g_arg = nullptr;
+
+/* x86-64 System V: callee-saved registers on the old stack, swap rsp, restore */
+__asm__(
+    ".text\n"
+    ".globl emu_switch\n"
+    ".type emu_switch,@function\n"
+    "emu_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n"
+    "  movq %rsi, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n"
+    "  ret\n"
+    ".size emu_switch,.-emu_switch\n");
+
+void yield_to_scheduler() { emu_switch(&cur->sp, sched_sp); }
+
+void warp_complete_if_ready(Warp &W) {
+	if (W.departing || !W.arrived || W.arrived != W.live) return;
+	for (int i = 0; i < 32; i++) W.snap[i] = ((W.arrived >> i) & 1) ? W.vals[i] : 0;
+	W.snap_mask = W.arrived;
+	W.departing = W.arrived;
+	W.arrived = 0;
+}
+
+static void fiber_main() {
+	g_thunk(g_arg);
+	Fiber *f = cur;
+	f->done = 1;
+	cta.alive--;
+	Warp &W = cta.w[f->warp];
+	W.live &= ~(1u << f->lane);
+	warp_complete_if_ready(W);
+	if (cta.alive > 0 && cta.bar_arrived == cta.alive) { /* the rest were waiting for this one */
+		cta.bar_arrived = 0;
+		cta.bar_gen++;
+	}
+	emu_switch(&f->sp, sched_sp);
+	abort(); /* a finished fiber is never resumed */
+}
+
+static bool runnable(const Fiber &f) {
+	switch (f.wait) {
+	case W_NONE: return true;
+	case W_BARRIER: return f.bar_gen != cta.bar_gen;
+	case W_WARP_ENTER: return cta.w[f.warp].departing == 0;
+	case W_WARP_RESULT: return (cta.w[f.warp].departing >> f.lane) & 1;
+	case W_WORD: return (*f.word & 1) != f.word_val;
+	}
+	return true;
+}
+
+void run_grid(dim3 grid, dim3 block, void (*thunk)(void *), void *arg) {
+	const size_t nt = (size_t)block.x * block.y * block.z;
+	if (nt > n_stacks) {
+		if (stacks) munmap(stacks, n_stacks * STACK);
+		stacks = (char *)mmap(nullptr, nt * STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+		if (stacks == MAP_FAILED) abort();
+		n_stacks = nt;
+	}
+	g_thunk = thunk;
+	g_arg = arg;
+	g_gridDim = grid;
+	g_blockDim = block;
+	cta.f.resize(nt);
+	cta.w.resize((nt + 31) / 32);
+	for (unsigned bx = 0; bx < grid.x; bx++) {
+		g_blockIdx = dim3(bx);
+		cta.alive = (int)nt;
+		cta.bar_arrived = 0;
+		cta.bar_gen = 0;
+		for (Warp &W : cta.w) memset(&W, 0, sizeof W);
+		for (size_t t = 0; t < nt; t++) {
+			Fiber &f = cta.f[t];
+			f.done = 0;
+			f.wait = W_NONE;
+			f.tid = dim3((unsigned)(t % block.x), (unsigned)(t / block.x));
+			f.lane = (int)(t & 31);
+			f.warp = (int)(t >> 5);
+			cta.w[f.warp].live |= 1u << f.lane;
+			/* initial frame: six callee-saved slots, then the entry point as return address;
+			 * after the `ret` rsp is 8 mod 16 as at any function entry */
+			uintptr_t top = ((uintptr_t)(stacks + (t + 1) * STACK)) & ~(uintptr_t)15;
+			void **sp = (void **)(top - 8);
+			*--sp = (void *)fiber_main;
+			for (int i = 0; i < 6; i++) *--sp = nullptr;
+			f.sp = sp;
+		}
+		int remaining = (int)nt;
+		while (remaining > 0) {
+			bool progress = false;
+			for (size_t t = 0; t < nt; t++) {
+				Fiber &f = cta.f[t];
+				if (f.done || !runnable(f)) continue;
+				f.wait = W_NONE;
+				cur = &f;
+				emu_switch(&sched_sp, f.sp);
+				progress = true;
+				if (f.done) remaining--;
+			}
+			if (!progress) {
+				fprintf(stderr, "emu: deadlock in CTA %u (%d threads parked)\n", bx, remaining);
+				abort();
+			}
+		}
+	}
+	cur = nullptr;
+}
+
+} /* namespace emu */

@@ -1,0 +1,71 @@
+"""The CUDA kernels' SOURCE executed on the CPU (tests/cpu_emu) against the oracle.
+
+No GPU here, so this is the only tier that can notice a logic error in the kernels
+(table layouts, pivot bookkeeping, shard exchange order) before the GPU box does:
+tests/cpu_emu/build_emu.py compiles gf2bv_b200/csrc/*.cu(h) with g++ against a
+stand-in for the CUDA runtime (threads of a CTA = fibers) and the GPU parity tests
+(tests/test_gpu_solver.py, tests/test_gpu_sharded.py -- same cases, same oracle
+checks) are run in a subprocess whose GF2B200_LIB points at that build.
+
+This is test infrastructure: the emulated library lives under tests/cpu_emu/_build,
+is never built by ``__graft_entry__.build()`` and never loaded by the package on its
+own; it says nothing about races, memory ordering or speed -- ``pytest -m gpu`` on
+a B200 stays the parity gate.  Both strip geometries the kernels can be compiled
+for are covered (GF2_STRIP_WORDS = 16: nine tables of 128-byte lines; 8: eight
+tables in line pairs).
+"""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "tests" / "cpu_emu"))
+
+# the heavy cases stay on the GPU; everything else is the GPU suite verbatim
+SUBSET = ("not 32768 and not mt19937 and not 8192 and not 1025-3000 and not 2000-1500 and not 4099 "
+          "and not 5000 and not 4096 and not 0.001 and not 2100")
+
+
+@pytest.fixture(scope="module")
+def emu_runs():
+    import build_emu
+
+    procs = {}
+    for sw in (16, 8):
+        lib = build_emu.build(sw)
+        env = dict(os.environ, GF2B200_LIB=str(lib), GF2_EMU_SMS="3")
+        procs[sw] = subprocess.Popen(
+            [sys.executable, "-m", "pytest", "tests/test_gpu_solver.py", "tests/test_gpu_sharded.py", "-m", "gpu",
+             "-x", "-q", "-p", "no:cacheprovider", "-k", SUBSET],
+            cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    out = {}
+    for sw, p in procs.items():
+        try:
+            text, _ = p.communicate(timeout=1500)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            text, _ = p.communicate()
+            text += "\n[timeout]"
+        out[sw] = (p.returncode, text)
+    return out
+
+
+@pytest.mark.parametrize("strip_words", [16, 8])
+def test_gpu_parity_suite_on_emulated_kernels(emu_runs, strip_words):
+    rc, text = emu_runs[strip_words]
+    tail = "\n".join(text.splitlines()[-25:])
+    assert rc == 0, tail
+    assert " passed" in tail and "failed" not in tail, tail
+
+
+def test_emulated_library_is_not_the_product():
+    """the package never points at the emulated build by itself"""
+    from gf2bv_b200 import _shim
+
+    if not os.environ.get("GF2B200_LIB"):
+        assert _shim.LIB_PATH == ROOT / "gf2bv_b200" / "libgf2b200.so"
+    src = (ROOT / "__graft_entry__.py").read_text() + (ROOT / "gf2bv_b200" / "_shim.py").read_text()
+    assert "cpu_emu" not in src
