@@ -603,7 +603,7 @@ static int forward_single(gf2b200_system *sys, long long *launches) {
 	const int nw = M.nw;
 	k_extract_pc<<<grid_for(M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(M, 0, h.d_pc[0], 0);
 	(*launches)++;
-	const int apply_cap = ctx->n_sm * 4;
+	const int apply_cap = ctx->n_sm * APPLY_CTAS_PER_SM;
 	const bool fused = !getenv("GF2B200_NO_FUSED_SELECT"); /* diagnostic switch */
 	for (int w = 0; w < nw; w++) {
 		u64 colmask = ~0ULL;
@@ -638,7 +638,7 @@ static int forward_sharded(gf2b200_system *sys, long long *launches, double *xby
 	const int G = ctx->world;
 	const int barriers = ctx->nccl ? 1 : 0;
 	const int nw = sys->sh[0].M.nw, ns = sys->sh[0].M.ns;
-	const int apply_cap = ctx->n_sm * 4;
+	const int apply_cap = ctx->n_sm * APPLY_CTAS_PER_SM;
 	for (Shard &h : sys->sh) {
 		k_extract_pc<<<grid_for(h.M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(h.M, 0, h.d_pc[0], 0);
 		(*launches)++;
@@ -685,14 +685,15 @@ static int forward_sharded(gf2b200_system *sys, long long *launches, double *xby
 	return GF2B200_OK;
 }
 
-/* blocked back-substitution of the particular solution into every shard's d_x */
-static int backward(gf2b200_system *sys, long long *launches, double *xbytes) {
+/* blocked back-substitution into every shard's d_x: the particular solution
+ * (freecol < 0) or the kernel vector of one free column */
+static int backward(gf2b200_system *sys, long long *launches, double *xbytes, long long freecol = -1) {
 	gf2b200_ctx *ctx = sys->ctx;
 	cudaStream_t st = ctx->stream;
 	const int nw = sys->sh[0].M.nw;
 	const bool sharded = ctx->world > 1;
 	const int nsp = (nw + BS_S - 1) / BS_S;
-	for (Shard &h : sys->sh) k_bs_init<<<(nw + 256) / 256, 256, 0, st>>>(h.d_x, nw);
+	for (Shard &h : sys->sh) k_bs_init<<<(nw + 256) / 256, 256, 0, st>>>(h.d_x, nw, freecol);
 	for (int P = nsp - 1; P >= 0; --P) {
 		for (Shard &h : sys->sh)
 			k_bs_outer<<<BS_S * 64 * 32 / 256, 256, 0, st>>>(h.M, h.d_hist_r, h.d_hist_pm,
@@ -839,8 +840,6 @@ extern "C" int gf2b200_system_result(gf2b200_system *sys, int mode, gf2b200_resu
 	memset(out, 0, sizeof *out);
 	if (mode != 0 && mode != 1) return fail(ctx, GF2B200_EINVAL, "Invalid mode");
 	if (!sys->eliminated) return fail(ctx, GF2B200_EINVAL, "system_result before system_eliminate");
-	if (mode == 1 && ctx->world > 1)
-		return fail(ctx, GF2B200_EINVAL, "kernel basis (mode 1) is not available on a sharded system");
 	Shard &h = sys->sh[0];
 	const Mat &M = h.M;
 	const int nw = M.nw;
@@ -877,6 +876,34 @@ extern "C" int gf2b200_system_result(gf2b200_system *sys, int mode, gf2b200_resu
 		if (!out->basis) {
 			gf2b200_result_free(out);
 			return fail(ctx, GF2B200_ENOMEM, "malloc basis");
+		}
+		if (ctx->world > 1) {
+			/* row-sharded system: one blocked back-substitution per free column over the
+			 * shards' echelon rows (same kernels and slab exchange as the particular
+			 * solution; every rank of an NCCL context calls this together and gets the
+			 * whole basis).  d_x is restored to the particular solution afterwards. */
+			long long launches = 0;
+			double xbytes = 0;
+			int rc = GF2B200_OK;
+			for (long long i = 0; i < d && !rc; i++) {
+				rc = backward(sys, &launches, &xbytes, sigma[r + i]);
+				if (!rc)
+					CK(ctx, cudaMemcpyAsync(out->basis + i * nw, h.d_x, (size_t)nw * 8, cudaMemcpyDeviceToHost,
+					                        ctx->stream));
+			}
+			for (Shard &sh : sys->sh) {
+				static const u64 one = 1;
+				CK(ctx, cudaMemcpyAsync(sh.d_x, out->origin, (size_t)nw * 8, cudaMemcpyHostToDevice, ctx->stream));
+				CK(ctx, cudaMemcpyAsync(sh.d_x + nw, &one, 8, cudaMemcpyHostToDevice, ctx->stream));
+			}
+			CK(ctx, cudaStreamSynchronize(ctx->stream));
+			if (rc) {
+				gf2b200_result_free(out);
+				return rc;
+			}
+			out->kernel_dim = d;
+			out->status = GF2B200_OK;
+			return GF2B200_OK;
 		}
 		size_t xs_bytes = (size_t)M.ns * SBYTES;
 		if (xs_bytes > 200 * 1024) {

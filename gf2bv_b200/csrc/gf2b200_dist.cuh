@@ -401,7 +401,7 @@ k_bs_outer(Mat M, const long long *__restrict__ hist_r, const u64 *__restrict__ 
 	{
 		const int wd = P * BS_S + lane;
 		const u64 v = (wd <= M.nw) ? M.base[widx(M, row, wd)] : 0;
-		const int bpar = (wd == M.nw) ? (int)(v & 1) : 0;
+		const int bpar = (wd == M.nw) ? (int)(v & x[M.nw] & 1) : 0;
 		par ^= __reduce_or_sync(0xffffffffu, bpar);
 		out[lane] = (wd < M.nw) ? v : 0;
 	}
@@ -415,10 +415,12 @@ k_bs_inner(const u64 *__restrict__ slab_all, const u64 *__restrict__ hist_pm,
 	__shared__ u64 xs[BS_S];
 	__shared__ unsigned long long newbits;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid < BS_S) xs[tid] = 0;
+	const int nwp = min(BS_S, nw - P * BS_S);
+	/* the free-variable bits of these words (all 0 for the particular solution, one
+	 * bit set somewhere for a kernel vector) are part of the right-hand side */
+	if (tid < BS_S) xs[tid] = (tid < nwp) ? x[P * BS_S + tid] : 0;
 	if (tid == 0) newbits = 0;
 	__syncthreads();
-	const int nwp = min(BS_S, nw - P * BS_S);
 	for (int wp = nwp - 1; wp >= 0; --wp) {
 		const int w = P * BS_S + wp;
 		const u64 pm = hist_pm[w];
@@ -426,7 +428,9 @@ k_bs_inner(const u64 *__restrict__ slab_all, const u64 *__restrict__ hist_pm,
 		for (int j = warp; j < k; j += 32) {
 			const int src = hist_owner ? hist_owner[(long long)w * 64 + j] : 0;
 			const u64 *row = slab_all + ((long long)src * (BS_S * 64) + wp * 64 + j) * BS_W;
-			u64 a = (lane > wp) ? (row[lane] & xs[lane]) : 0;
+			/* word wp itself: the row is 0 at the panel's other pivot columns (RREF inside
+			 * the panel) and xs[wp] holds only free-variable bits until the panel is done */
+			u64 a = (lane >= wp) ? (row[lane] & xs[lane]) : 0;
 			int par = __popcll(a) & 1;
 			par = __reduce_xor_sync(0xffffffffu, par) ^ (int)(row[BS_S] & 1);
 			if (lane == 0 && par) {
@@ -437,7 +441,7 @@ k_bs_inner(const u64 *__restrict__ slab_all, const u64 *__restrict__ hist_pm,
 		}
 		__syncthreads();
 		if (tid == 0) {
-			xs[wp] = newbits;
+			xs[wp] |= newbits;
 			newbits = 0;
 		}
 		__syncthreads();
@@ -445,10 +449,17 @@ k_bs_inner(const u64 *__restrict__ slab_all, const u64 *__restrict__ hist_pm,
 	if (tid < nwp) x[P * BS_S + tid] = xs[tid];
 }
 
-/* x[0..nw) = 0, x[nw] = 1 (the b column's "unknown") */
-__global__ void k_bs_init(u64 *x, int nw) {
+/* Right-hand side of the back-substitution.  freecol < 0: the particular solution,
+ * x[0..nw) = 0 and x[nw] = 1 (the b column's "unknown").  freecol >= 0: the kernel
+ * vector that is 1 at that free column and 0 at the other free columns
+ * (_internal.c:330-348), x = e_freecol and x[nw] = 0 (homogeneous). */
+__global__ void k_bs_init(u64 *x, int nw, long long freecol) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i <= nw) x[i] = (i == nw) ? 1 : 0;
+	if (i > nw) return;
+	u64 v = 0;
+	if (freecol < 0) v = (i == nw) ? 1 : 0;
+	else if (i == (int)(freecol >> 6)) v = 1ULL << (freecol & 63);
+	x[i] = v;
 }
 
 } /* namespace gf2b200 */

@@ -47,7 +47,7 @@ typedef unsigned long long u64;
  * lookup tables of whole 128-byte lines; 8 -> 64-byte strips, eight tables stored
  * as four line PAIRS (see k_sweep). */
 #ifndef GF2_STRIP_WORDS
-#define GF2_STRIP_WORDS 16
+#define GF2_STRIP_WORDS 8
 #endif
 #if GF2_STRIP_WORDS == 16
 #define SW 16        /* 64-bit words per strip piece */
@@ -424,6 +424,9 @@ k_select(Mat M, u64 *__restrict__ pc, int w, u64 colmask, SolverState *st, Panel
  * positions.  512 threads = 64 rows x 8 x 16 B.
  * ---------------------------------------------------------------------- */
 #define APPLY_THREADS (64 * SQ)
+#ifndef APPLY_CTAS_PER_SM
+#define APPLY_CTAS_PER_SM (2048 / APPLY_THREADS) /* grid cap: a full SM of threads, strips strided over the grid */
+#endif
 
 __global__ void __launch_bounds__(APPLY_THREADS)
 k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s0) {
@@ -498,6 +501,12 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
 #endif
 #define SWEEP_RU (SWEEP_THREADS / SQ * SWEEP_U) /* rows per unit */
 #define EBUF_Q (64 * SQ) /* uint4 per strip in ebuf */
+#ifndef SWEEP_PREFETCH
+#define SWEEP_PREFETCH (SW == 8) /* loads before the table build + early E-tile TMA (needs E outside the tables) */
+#endif
+#if SWEEP_PREFETCH && SW == 16
+#error "SWEEP_PREFETCH needs the E tile outside the tables (GF2_STRIP_WORDS=8)"
+#endif
 #if SW == 16
 #define SWEEP_LINES (8 * 128 + 256)
 #define SWEEP_PARTS (8 * 24 + 32)
@@ -516,7 +525,9 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
  * 164 KiB carve-out. */
 #define SWEEP_LINES (4 * 256)
 #define SWEEP_PSTRIDE 132 /* uint4 per table in P: 32 entries x 4 chunks + 64 B skew (tables 2p / 2p+1 on opposite bank halves) */
-#define SWEEP_SMEM (SWEEP_LINES * 128 + EBUF_Q * 16 + 8 * SWEEP_PSTRIDE * 16 + 16)
+#define SWEEP_BUILD_BYTES (EBUF_Q * 16 + 8 * SWEEP_PSTRIDE * 16)
+#define SWEEP_SCRATCH_BYTES 24576 /* E | P during a build, the fused pivot search's SelectSmem otherwise */
+#define SWEEP_SMEM (SWEEP_LINES * 128 + SWEEP_SCRATCH_BYTES + 16)
 #endif
 
 #ifndef GF2_EMU
@@ -630,7 +641,8 @@ static_assert(EBUF_Q * 16 <= 128 * 128, "the E tile must fit inside field 0's li
  * Step 1: per table t (columns 8t..8t+7) 16 combinations of its low 4 columns and
  * 16 of its high 4 (one item per thread).  Step 2: entry e = lo[e & 15] ^ hi[e >> 4],
  * written into the half-line of its table.  Ends with a __syncthreads. */
-__device__ __forceinline__ void sweep_build_tables(uint4 *TD, uint4 *P, const uint4 *E, int tid) {
+__device__ __forceinline__ void sweep_build_tables(uint4 *TD, uint4 *P, uint4 *E, int tid,
+                                                   const uint4 *next_tile, void *bar) {
 	{
 		const int t = tid >> 7, e5 = (tid >> 2) & 31, c4 = tid & 3;
 		const int col0 = 8 * t + (e5 & 16 ? 4 : 0), e = e5 & 15;
@@ -641,20 +653,30 @@ __device__ __forceinline__ void sweep_build_tables(uint4 *TD, uint4 *P, const ui
 		P[t * SWEEP_PSTRIDE + e5 * 4 + c4] = acc;
 	}
 	__syncthreads();
+	/* E is dead from here on: fetch the tile of the strip this CTA enters next */
+	if (next_tile && tid == 0) {
+		mbar_expect_tx(bar, EBUF_Q * 16);
+		tma_bulk_g2s(E, next_tile, EBUF_Q * 16, bar);
+	}
+	/* thread = (chunk, table of the pair, low nibble, half of the high nibbles, pair):
+	 * the low-nibble part is read once, then 8 entries are one LDS + one STS each; the 8
+	 * threads of a quarter-warp write one whole 128-byte line */
+	{
+		const int c4 = tid & 3, tpar = (tid >> 2) & 1, lo = (tid >> 3) & 15, hh = (tid >> 7) & 1, pr = tid >> 8;
+		const uint4 *Pt = P + (2 * pr + tpar) * SWEEP_PSTRIDE + c4;
+		const uint4 base = Pt[lo * 4];
+		uint4 *dst = TD + ((pr * 256 + hh * 128 + lo) * 8 + tpar * 4 + c4);
 #pragma unroll
-	for (int q = 0; q < SWEEP_LINES * 8 / SWEEP_THREADS; q++) {
-		const int it = tid + q * SWEEP_THREADS; /* (line, chunk of the 128-byte line) */
-		const int L = it >> 3, c8 = it & 7;
-		const int t = 2 * (L >> 8) + (c8 >> 2), e = L & 255, c4 = c8 & 3;
-		uint4 a = P[t * SWEEP_PSTRIDE + (e & 15) * 4 + c4];
-		xor4(a, P[t * SWEEP_PSTRIDE + (16 + (e >> 4)) * 4 + c4]);
-		TD[it] = a;
+		for (int j = 0; j < 8; j++) {
+			uint4 a = Pt[(16 + hh * 8 + j) * 4];
+			xor4(a, base);
+			dst[j * 16 * 8] = a; /* entry e = (hh*8 + j)*16 + lo */
+		}
 	}
 	__syncthreads();
 }
 
-static_assert(sizeof(SelectSmem) <= SWEEP_LINES * 128, "pivot-search scratch must fit inside the tables");
-static_assert(SWEEP_THREADS == 8 * 32 * 4, "one partial-table item per thread");
+static_assert(SWEEP_THREADS == 8 * 32 * 4, "one partial-table item per thread; (4 chunks, 2, 16, 2, 4 pairs) in the second step");
 #endif
 #ifndef SWEEP_SEL_PAD
 #define SWEEP_SEL_PAD 4 /* units CTA 0 is spared to make room for the fused pivot search */
@@ -673,10 +695,16 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 #else
 	uint4 *E = TD + SWEEP_LINES * 8; /* the E tile and the partial tables follow the tables */
 	uint4 *P = E + EBUF_Q;
-	u64 *bar = reinterpret_cast<u64 *>(P + 8 * SWEEP_PSTRIDE);
+	u64 *bar = reinterpret_cast<u64 *>(smem_raw + SWEEP_LINES * 128 + SWEEP_SCRATCH_BYTES);
+	static_assert(SWEEP_BUILD_BYTES <= SWEEP_SCRATCH_BYTES && sizeof(SelectSmem) <= SWEEP_SCRATCH_BYTES,
+	              "build scratch and pivot-search scratch share the region behind the tables");
 #endif
 	/* scratch of the fused pivot search of panel w+1 (pd_next != nullptr): over the tables */
+#if SW == 16
 	SelectSmem &S = *reinterpret_cast<SelectSmem *>(smem_raw);
+#else
+	SelectSmem &S = *reinterpret_cast<SelectSmem *>(smem_raw + SWEEP_LINES * 128); /* tables stay intact */
+#endif
 
 	const int tid = threadIdx.x;
 	const int k = pd->k;
@@ -725,9 +753,14 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 	const unsigned bsel = h ? 0x2301u : 0x3210u;
 #endif
 
+#if SWEEP_PREFETCH
+	const int s_last = s0 + (int)((u1 - 1) / nchunks); /* last strip this CTA touches */
+	int fetched = -1;                                  /* strip whose E tile is already on its way */
+#endif
 	for (long long u = u0; u < u1; ++u) {
 		const int s = s0 + (int)(u / nchunks);
 		const long long chunk = u % nchunks;
+#if !SWEEP_PREFETCH
 		if (s != cur) {
 			__syncthreads(); /* everyone is done with the previous tables */
 			if (tid == 0) {
@@ -736,9 +769,14 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 			}
 			mbar_wait(bar, phase);
 			phase ^= 1;
+#if SW == 16
 			sweep_build_tables(TD, P, E, tid);
+#else
+			sweep_build_tables(TD, P, E, tid, nullptr, bar);
+#endif
 			cur = s;
 		}
+#endif
 		const long long row0 = r1 + chunk * SWEEP_RU + rl;
 		const bool force = (s == snext);
 		uint4 *p = mb + ((long long)s * M.mp + row0) * SQ + ch;
@@ -756,6 +794,25 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 			act[q] = (row < m) && (cf[q] != 0 || force);
 			if (act[q]) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ);
 		}
+#if SWEEP_PREFETCH
+		/* Entering a new strip: this unit's row pieces are already in flight, so the
+		 * table build overlaps their latency, and the strip's E tile was requested
+		 * during the previous build (not for the unit that carries the fused pivot
+		 * search: its scratch and the rebuild afterwards want a quiet barrier). */
+		if (s != cur) {
+			__syncthreads(); /* everyone is done with the previous tables */
+			if (fetched != s && tid == 0) {
+				mbar_expect_tx(bar, EBUF_Q * 16);
+				tma_bulk_g2s(E, ebuf + (long long)s * EBUF_Q, EBUF_Q * 16, bar);
+			}
+			mbar_wait(bar, phase);
+			phase ^= 1;
+			const bool more = (s < s_last) && !(pd_next && u == 0);
+			sweep_build_tables(TD, P, E, tid, more ? ebuf + (long long)(s + 1) * EBUF_Q : nullptr, bar);
+			fetched = more ? s + 1 : -1;
+			cur = s;
+		}
+#endif
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {
 			if (!act[q]) continue;
@@ -804,7 +861,9 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 			 * The rows' other strips are complete by the time k_apply runs. */
 			__threadfence();
 			__syncthreads(); /* also: every lookup of this unit is done, the tables may be clobbered */
+#if SW == 16
 			cur = -1;        /* ... and are rebuilt before the next unit */
+#endif
 			select_init(S);
 			__syncthreads();
 			const long long lim = min(m, r1 + (long long)SWEEP_RU);

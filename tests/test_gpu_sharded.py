@@ -70,10 +70,35 @@ def test_sharded_pivots_concentrated_in_one_shard(sharded):
     _check(sharded.solve(A2, b2, n, 0), oracle.solve_packed(A2, b2, n, 0))
 
 
-def test_sharded_mode1_is_refused(sharded):
-    A, b = _rand_system(random.Random(1), 70, 64, consistent=True)
-    with pytest.raises(_shim.Gf2b200Error, match="mode 1"):
-        sharded.solve(A, b, 64, 1)
+@pytest.mark.parametrize("m,n,cap", [
+    (70, 64, None), (300, 200, 190), (700, 640, 620), (2200, 2110, None), (2300, 2100, 2070),
+    # one back-substitution per free column: the large nullities are left to the GPU
+    pytest.param(1300, 2100, 900, id="bignull-1300-2100-900"), pytest.param(64, 4096, 20, id="bignull-64-4096-20"),
+    pytest.param(1111, 999, 1, id="bignull-1111-999-1")])
+def test_sharded_kernel_basis(sharded, m, n, cap):
+    """mode 1 on a sharded system: one blocked back-substitution per free column;
+    basis values AND order (M4RI's sigma order) equal the oracle's, and a mode-0
+    result taken afterwards is still the particular solution"""
+    rnd = random.Random(cap or 0 + m)
+    A, b = _rand_system(rnd, m, n, rank_cap=cap, consistent=True)
+    want = oracle.solve_packed(A, b, n, 1)
+    ss = sharded.system(m, n)
+    ss.load_host(A, b)
+    ss.eliminate()
+    got = ss.result(1)
+    _check(got, want)
+    assert got.basis.shape == want.basis.shape and np.array_equal(got.basis, want.basis)
+    _check(ss.result(0), want)
+    got2 = ss.result(1)
+    assert np.array_equal(got2.basis, want.basis) and np.array_equal(got2.origin, want.origin)
+
+
+def test_sharded_kernel_basis_homogeneous(sharded):
+    A, _ = _rand_system(random.Random(9), 660, 700, consistent=True)
+    want = oracle.solve_packed(A, None, 700, 1)
+    got = sharded.solve(A, None, 700, 1)
+    _check(got, want)
+    assert np.array_equal(got.basis, want.basis)
 
 
 @pytest.mark.parametrize("n,seed", [(4096, 1), (5000, 2), (8192, 3)])
