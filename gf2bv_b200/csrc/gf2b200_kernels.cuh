@@ -247,9 +247,13 @@ __device__ __forceinline__ void wb_store(const WarpBasis &W, u64 *B, u64 *TB, in
 /* v, tv, row uniform across the warp.  Returns true if v raised the rank. */
 __device__ __forceinline__ bool wb_insert(WarpBasis &W, int *sel, u64 v, u64 tv, int row, int lane) {
 	const u64 m0 = 0ULL - ((v >> lane) & 1), m1 = 0ULL - ((v >> (lane + 32)) & 1);
-	v ^= warp_xor64((W.B0 & m0) ^ (W.B1 & m1));
+	/* both folds are issued together (four independent REDUX): this loop is a serial
+	 * chain on the critical path of every panel, one REDUX latency per candidate */
+	const u64 rv = warp_xor64((W.B0 & m0) ^ (W.B1 & m1));
+	const u64 rt = warp_xor64((W.T0 & m0) ^ (W.T1 & m1));
+	v ^= rv;
 	if (!v) return false;
-	tv ^= warp_xor64((W.T0 & m0) ^ (W.T1 & m1));
+	tv ^= rt;
 	const int c = __ffsll((long long)v) - 1;
 	tv ^= 1ULL << W.nsel;
 	if ((W.B0 >> c) & 1) { W.B0 ^= v; W.T0 ^= tv; }
@@ -314,8 +318,16 @@ __device__ __forceinline__ void select_scan(SelectSmem &S, const u64 *__restrict
 			/* survivors, one at a time, against the register-resident basis */
 			WarpBasis W;
 			wb_load(W, S.B, S.TB, pm, S.nsel, lane);
-			for (int q = 0; q < total && W.pm != colmask; q++)
-				wb_insert(W, S.sel, S.qv[q], S.qtv[q], S.qrow[q], lane);
+			/* the next candidate is read while the current one is inserted */
+			u64 cv = S.qv[0], ct = S.qtv[0];
+			int cr = S.qrow[0];
+			for (int q = 0; q < total && W.pm != colmask; q++) {
+				const int qn = min(q + 1, SEL_THREADS - 1);
+				const u64 nv = S.qv[qn], nt = S.qtv[qn];
+				const int nr = S.qrow[qn];
+				wb_insert(W, S.sel, cv, ct, cr, lane);
+				cv = nv; ct = nt; cr = nr;
+			}
 			wb_store(W, S.B, S.TB, lane);
 			__syncwarp(); /* every lane has read S.nsel / S.pm before lane 0 replaces them */
 			if (lane == 0) {
@@ -501,11 +513,18 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
 #endif
 #define SWEEP_RU (SWEEP_THREADS / SQ * SWEEP_U) /* rows per unit */
 #define EBUF_Q (64 * SQ) /* uint4 per strip in ebuf */
-#ifndef SWEEP_PREFETCH
-#define SWEEP_PREFETCH (SW == 8) /* loads before the table build + early E-tile TMA (needs E outside the tables) */
+/* Two scheduling switches of k_sweep at a strip change (64-byte strips only: they need
+ * the E tile outside the tables).  Measured on one box at n = 131072 (profiles/r01e_ab.txt):
+ * both on 626 ms per solve, both off 620 ms -- so both default to off; the A/B of each one
+ * alone is in profiles/. */
+#ifndef SWEEP_EARLY_LOADS
+#define SWEEP_EARLY_LOADS 0 /* issue a unit's row loads before the table build of its strip */
 #endif
-#if SWEEP_PREFETCH && SW == 16
-#error "SWEEP_PREFETCH needs the E tile outside the tables (GF2_STRIP_WORDS=8)"
+#ifndef SWEEP_EARLY_TILE
+#define SWEEP_EARLY_TILE 0 /* request the next strip's E tile (TMA) during the current build */
+#endif
+#if (SWEEP_EARLY_LOADS || SWEEP_EARLY_TILE) && SW == 16
+#error "SWEEP_EARLY_LOADS / SWEEP_EARLY_TILE need GF2_STRIP_WORDS=8"
 #endif
 #if SW == 16
 #define SWEEP_LINES (8 * 128 + 256)
@@ -679,7 +698,7 @@ __device__ __forceinline__ void sweep_build_tables(uint4 *TD, uint4 *P, uint4 *E
 static_assert(SWEEP_THREADS == 8 * 32 * 4, "one partial-table item per thread; (4 chunks, 2, 16, 2, 4 pairs) in the second step");
 #endif
 #ifndef SWEEP_SEL_PAD
-#define SWEEP_SEL_PAD 4 /* units CTA 0 is spared to make room for the fused pivot search */
+#define SWEEP_SEL_PAD 6 /* units CTA 0 is spared to make room for the fused pivot search (2: 631, 4: 626, 6: 622 ms) */
 #endif
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
@@ -753,29 +772,42 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 	const unsigned bsel = h ? 0x2301u : 0x3210u;
 #endif
 
-#if SWEEP_PREFETCH
+#if SW == 8
 	const int s_last = s0 + (int)((u1 - 1) / nchunks); /* last strip this CTA touches */
 	int fetched = -1;                                  /* strip whose E tile is already on its way */
 #endif
+	/* (re)build the tables when unit u lies in another strip than the previous one */
+	auto enter_strip = [&](int s, long long u) {
+		if (s == cur) return;
+		__syncthreads(); /* everyone is done with the previous tables */
+#if SW == 16
+		if (tid == 0) {
+			mbar_expect_tx(bar, EBUF_Q * 16);
+			tma_bulk_g2s(E, ebuf + (long long)s * EBUF_Q, EBUF_Q * 16, bar);
+		}
+		mbar_wait(bar, phase);
+		phase ^= 1;
+		sweep_build_tables(TD, P, E, tid);
+#else
+		if (fetched != s && tid == 0) {
+			mbar_expect_tx(bar, EBUF_Q * 16);
+			tma_bulk_g2s(E, ebuf + (long long)s * EBUF_Q, EBUF_Q * 16, bar);
+		}
+		mbar_wait(bar, phase);
+		phase ^= 1;
+		/* not for the unit that carries the fused pivot search: its scratch shares the
+		 * E region and wants a quiet barrier */
+		const bool more = SWEEP_EARLY_TILE && (s < s_last) && !(pd_next && u == 0);
+		sweep_build_tables(TD, P, E, tid, more ? ebuf + (long long)(s + 1) * EBUF_Q : nullptr, bar);
+		fetched = more ? s + 1 : -1;
+#endif
+		cur = s;
+	};
 	for (long long u = u0; u < u1; ++u) {
 		const int s = s0 + (int)(u / nchunks);
 		const long long chunk = u % nchunks;
-#if !SWEEP_PREFETCH
-		if (s != cur) {
-			__syncthreads(); /* everyone is done with the previous tables */
-			if (tid == 0) {
-				mbar_expect_tx(bar, EBUF_Q * 16);
-				tma_bulk_g2s(E, ebuf + (long long)s * EBUF_Q, EBUF_Q * 16, bar);
-			}
-			mbar_wait(bar, phase);
-			phase ^= 1;
-#if SW == 16
-			sweep_build_tables(TD, P, E, tid);
-#else
-			sweep_build_tables(TD, P, E, tid, nullptr, bar);
-#endif
-			cur = s;
-		}
+#if !SWEEP_EARLY_LOADS
+		enter_strip(s, u);
 #endif
 		const long long row0 = r1 + chunk * SWEEP_RU + rl;
 		const bool force = (s == snext);
@@ -794,24 +826,8 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 			act[q] = (row < m) && (cf[q] != 0 || force);
 			if (act[q]) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ);
 		}
-#if SWEEP_PREFETCH
-		/* Entering a new strip: this unit's row pieces are already in flight, so the
-		 * table build overlaps their latency, and the strip's E tile was requested
-		 * during the previous build (not for the unit that carries the fused pivot
-		 * search: its scratch and the rebuild afterwards want a quiet barrier). */
-		if (s != cur) {
-			__syncthreads(); /* everyone is done with the previous tables */
-			if (fetched != s && tid == 0) {
-				mbar_expect_tx(bar, EBUF_Q * 16);
-				tma_bulk_g2s(E, ebuf + (long long)s * EBUF_Q, EBUF_Q * 16, bar);
-			}
-			mbar_wait(bar, phase);
-			phase ^= 1;
-			const bool more = (s < s_last) && !(pd_next && u == 0);
-			sweep_build_tables(TD, P, E, tid, more ? ebuf + (long long)(s + 1) * EBUF_Q : nullptr, bar);
-			fetched = more ? s + 1 : -1;
-			cur = s;
-		}
+#if SWEEP_EARLY_LOADS
+		enter_strip(s, u); /* this unit's row pieces are already in flight during the build */
 #endif
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {
@@ -859,8 +875,10 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 			 * sweeping; a full set (the usual case on dense systems) or an exhausted
 			 * row range makes the description final and turns k_select into a no-op.
 			 * The rows' other strips are complete by the time k_apply runs. */
-			__threadfence();
-			__syncthreads(); /* also: every lookup of this unit is done, the tables may be clobbered */
+			/* the pc_next words these rows just received are read back by this CTA only:
+			 * the barrier orders them; the rest of the grid meets them at the kernel boundary */
+			__threadfence_block();
+			__syncthreads(); /* also: every lookup of this unit is done (SW = 16: the tables may be clobbered) */
 #if SW == 16
 			cur = -1;        /* ... and are rebuilt before the next unit */
 #endif

@@ -61,7 +61,7 @@ typedef struct {
 	double ms_forward;
 	double ms_backward;
 	double ms_sweep;        /* sum of k_sweep durations (profile mode only, else 0) */
-	double sweep_bytes;     /* algorithmic bytes of all sweeps: sum 2 * rows * 128 B * strips */
+	double sweep_bytes;     /* algorithmic bytes of all sweeps: sum 2 * rows * strip bytes * strips */
 	double exchange_bytes;  /* multi-GPU: bytes this rank contributed to collectives */
 	int64_t sweep_launches; /* sweeps that had work (k > 0 and active rows) */
 	int64_t kernel_launches; /* all kernels launched by the elimination */
@@ -118,7 +118,8 @@ void gf2b200_result_free(gf2b200_result *res);
 /* ---- device-resident systems -------------------------------------------- */
 /* m, n are GLOBAL sizes; with a dist context each rank holds rows
  * [rank*m/world, (rank+1)*m/world) of the global system.  On a sharded system
- * (dist or loopback) system_result supports mode 0 only. */
+ * (dist or loopback) system_result(mode 1) runs one blocked back-substitution per
+ * free column; on a dist context every rank must call it and gets the whole basis. */
 int gf2b200_system_create(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2b200_system **out);
 void gf2b200_system_destroy(gf2b200_system *sys);
 int64_t gf2b200_system_local_rows(const gf2b200_system *sys);

@@ -12,7 +12,7 @@ T0=$(date +%s)
 stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a $O/timeline_$R.txt; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > $O/smi_$R.txt; nproc >> $O/smi_$R.txt
 stamp "pytest -m gpu (default build)"
-timeout 240 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee $O/pytest_gpu_$R.txt
+timeout 240 python -m pytest tests -m gpu -x -q ${PYTEST_K:+-k "$PYTEST_K"} 2>&1 | tail -6 | tee $O/pytest_gpu_$R.txt
 stamp "smoke"
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $O/smoke_$R.txt
 stamp "A/B n=131072"

@@ -2,7 +2,7 @@
 """Turn the ncu outputs a gpurun call left in gpurun_out/ into the tracked
 summaries under profiles/.
 
-    python scripts/summarize_profiles.py <round-tag> <launches.csv> <sweep.ncu-rep> [first_panel]
+    python scripts/summarize_profiles.py <round-tag> <launches.csv> <sweep.ncu-rep> [first_panel] [n] [strip_words]
 
 Writes profiles/<tag>_launches.md (per-kernel totals and shares of one bench step),
 profiles/<tag>_sweep_ncu.md (the metrics of the captured k_sweep launches) and
@@ -20,6 +20,8 @@ ROOT = Path(__file__).resolve().parents[1]
 tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
 first_panel = int(sys.argv[4]) if len(sys.argv) > 4 else 20
 n = int(sys.argv[5]) if len(sys.argv) > 5 else 131072
+SWORDS = int(sys.argv[6]) if len(sys.argv) > 6 else 8  # GF2_STRIP_WORDS of the profiled build
+SBYTES, SSHIFT = SWORDS * 8, SWORDS.bit_length() - 1
 out = ROOT / "profiles"
 out.mkdir(exist_ok=True)
 
@@ -40,7 +42,11 @@ for r in rows[hi + 1:]:
     a[1] += v
     a[2] = max(a[2], v)
 tot = sum(v[1] for v in agg.values())
-lines = [f"# {tag}: ncu launch list of one bench step (n={n}, 1 GPU)", "",
+n_sweeps = agg["k_sweep"][0] if "k_sweep" in agg else 0
+full_step = n_sweeps >= (n + 63) // 64
+lines = [f"# {tag}: ncu launch list of one bench step (n={n}, 1 GPU)" +
+         ("" if full_step else f" -- PARTIAL: the first {n_sweeps} of {(n + 63) // 64} panels "
+          "(ncu costs ~0.17 s per launch on this pool; the GPU budget of the round did not allow all 6185 launches)"), "",
          "`ncu --metrics gpu__time_duration.sum --clock-control none` around `python bench.py --steps 1 --warmup 1 "
          "--no-e2e --no-cpu`; launches are serialised and cold-cache, so compare SHARES with bench.py's "
          "`roofline.sweep_share_of_step`, not absolute times.", "",
@@ -65,7 +71,9 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed", "launch__shared_mem_config_size"]
 md = [f"# {tag}: `ncu --set full --clock-control none` of k_sweep (n={n}, panels {first_panel}..)", "",
       "| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |",
       "|---|---|" + "---|" * len(data)]
@@ -89,15 +97,15 @@ def scale(name):
 rd = [fnum(x) * scale("dram__bytes_read.sum") for x in vals["dram__bytes_read.sum"]]
 wr = [fnum(x) * scale("dram__bytes_write.sum") for x in vals["dram__bytes_write.sum"]]
 nw = (n + 63) // 64
-ns = (nw + 1 + 15) // 16
+ns = (nw + 1 + SWORDS - 1) // SWORDS
 alg = []
 for j in range(len(data)):
     w = first_panel + j
     r1 = 64 * (w + 1)
-    alg.append(2.0 * (n - r1) * 128.0 * (ns - ((w + 1) >> 4)))
+    alg.append(2.0 * (n - r1) * SBYTES * (ns - ((w + 1) >> SSHIFT)))
 ratio = sum(rd[j] + wr[j] for j in range(len(data))) / sum(alg)
 md += ["", f"DRAM traffic per launch (read+write): {[round((rd[j] + wr[j]) / 1e9, 3) for j in range(len(data))]} GB; "
-           f"algorithmic bytes of the same launches (2 * rows * 128 B * strips): {[round(a / 1e9, 3) for a in alg]} GB; "
+           f"algorithmic bytes of the same launches (2 * rows * {SBYTES} B * strips): {[round(a / 1e9, 3) for a in alg]} GB; "
            f"traffic / algorithmic = {ratio:.3f}"]
 wf = [fnum(x) for x in vals["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]]
 bc = [fnum(x) for x in vals["l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]]
