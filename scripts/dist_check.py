@@ -87,6 +87,13 @@ for m, n, cap in cases:
         s.eliminate()
         got = s.result(0)
         agree(got, oracle.solve_packed(A, b, n, 0), f"host-loaded {m}x{n} cap={cap} consistent={consistent}")
+        if consistent and cap in (65, 700, 20):
+            # kernel basis on the sharded system: collective, every rank gets the whole basis
+            got1, want1 = s.result(1), oracle.solve_packed(A, b, n, 1)
+            agree(got1, want1, f"mode 1 {m}x{n} cap={cap}")
+            if not np.array_equal(got1.basis, want1.basis):
+                ok = False
+                print(f"[rank {rank}] MISMATCH kernel basis {m}x{n} cap={cap}", flush=True)
         s.close()
 
 flag = torch.tensor([0 if ok else 1], device="cuda")

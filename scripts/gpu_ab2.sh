@@ -16,8 +16,8 @@ timeout 240 python -m pytest tests -m gpu -x -q ${PYTEST_K:+-k "$PYTEST_K"} 2>&1
 stamp "smoke"
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $O/smoke_$R.txt
 stamp "A/B n=131072"
-LIBS="gf2bv_b200/libgf2b200.so $(ls gf2bv_b200/variants/*.so)"
-for rep in 1 2; do for so in $LIBS; do
+LIBS=${AB_LIBS:-"gf2bv_b200/libgf2b200.so $(ls gf2bv_b200/variants/*.so)"}
+for rep in $(seq 1 ${AB_REPS:-2}); do for so in $LIBS; do
   echo -n "$(basename $so) " | tee -a $O/ab_$R.txt
   GF2B200_LIB=$PWD/$so timeout 60 python scripts/dev_bench.py 131072 1 2 2>&1 | grep ms_total | tail -1 | python -c "
 import json,sys
@@ -35,8 +35,8 @@ timeout 150 python bench.py --steps 3 --warmup 3 2> $O/bench_$R.err | tee $O/ben
 stamp "ncu full sweep"
 timeout 120 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 20 -c 3 \
     -o $O/sweep_$R python scripts/dev_bench.py 131072 0 1 > $O/ncu_full_$R.log 2>&1
-stamp "ncu launch list (first $NL launches)"
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c $NL --csv \
+[ "$NL" -gt 0 ] && stamp "ncu launch list (first $NL launches)"
+[ "$NL" -gt 0 ] && timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c $NL --csv \
     --log-file $O/launches_$R.csv python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > $O/bench_under_ncu_$R.log 2>&1
 stamp done
 ls -la $O
