@@ -514,14 +514,15 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
 #define SWEEP_RU (SWEEP_THREADS / SQ * SWEEP_U) /* rows per unit */
 #define EBUF_Q (64 * SQ) /* uint4 per strip in ebuf */
 /* Two scheduling switches of k_sweep at a strip change (64-byte strips only: they need
- * the E tile outside the tables).  Measured on one box at n = 131072 (profiles/r01e_ab.txt):
- * both on 626 ms per solve, both off 620 ms -- so both default to off; the A/B of each one
- * alone is in profiles/. */
+ * the E tile outside the tables).  A/B on one box at n = 131072 (profiles/r01f_ab.txt,
+ * r01e_ab.txt): neither 622.6 ms per solve, early tile alone 608.8 ms, both 626 ms --
+ * the early tile hides the TMA round trip of ~14 strip changes per CTA and launch, the
+ * early loads lengthen the build (registers held across it) by more than they hide. */
 #ifndef SWEEP_EARLY_LOADS
 #define SWEEP_EARLY_LOADS 0 /* issue a unit's row loads before the table build of its strip */
 #endif
 #ifndef SWEEP_EARLY_TILE
-#define SWEEP_EARLY_TILE 0 /* request the next strip's E tile (TMA) during the current build */
+#define SWEEP_EARLY_TILE (SW == 8) /* request the next strip's E tile (TMA) during the current build */
 #endif
 #if (SWEEP_EARLY_LOADS || SWEEP_EARLY_TILE) && SW == 16
 #error "SWEEP_EARLY_LOADS / SWEEP_EARLY_TILE need GF2_STRIP_WORDS=8"
