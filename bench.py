@@ -16,7 +16,7 @@ metric's target is quoted on); N > 1: n = 524288 row-sharded (configs[4]).
            extension makes in place of M4RI -- with HOST (pinned) A and b: H2D, layout,
            eliminate, back-substitute and D2H of the solution inside the timed region.
 `roofline`: k_sweep (the row-XOR sweep, the dominant kernel): algorithmic bytes
-           (2 * rows * 64 B * strips per launch) / CUDA-event duration of every
+           (2 * rows * 64 B * strips per launch; 64-byte strips) / CUDA-event duration of every
            sweep launch of one profiled step, against MEASURED_PEAKS.json hbm_gbs.
 `cpu_baseline`: the oracle's blocked Four-Russians port (oracle/gf2_oracle.c,
            "port": M4RI itself is absent from the image) on the host cores, on a
