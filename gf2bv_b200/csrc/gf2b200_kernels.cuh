@@ -8,12 +8,13 @@
  * 64-column panels designed around HBM streaming:
  *
  *   HBM layout ("strip-major"): the augmented matrix [A | b] is cut into column
- *   strips of SW = 16 words (128 B).  Strip s holds, for every row i, the 128-byte
- *   piece words 16s..16s+15 of that row, rows contiguous:  word(i, w) lives at
- *       base[((w / 16) * mp + i) * 16 + (w % 16)].
- *   A sweep work unit (one strip x 512 rows) is therefore ONE contiguous 64 KiB
+ *   strips of SW = 8 words (64 B; GF2_STRIP_WORDS = 16 keeps the first geometry).
+ *   Strip s holds, for every row i, the 64-byte piece words 8s..8s+7 of that row,
+ *   rows contiguous:  word(i, w) lives at
+ *       base[((w / SW) * mp + i) * SW + (w % SW)].
+ *   A sweep work unit (one strip x 1024 rows) is therefore ONE contiguous 64 KiB
  *   region: perfectly coalesced 128-bit loads/stores, no strided DRAM pages, and a
- *   row piece is exactly one 128-byte shared-memory line of the lookup tables.
+ *   row piece is half a 128-byte shared-memory line of the lookup tables.
  *   b sits alone in word nw (bit 0).
  *
  *   per panel (word column w):
@@ -23,15 +24,16 @@
  *               REDUX.XOR); yields <= 64 pivot rows, the pivot-column mask (= the
  *               panel's column rank profile) and the 64x64 transform TB that
  *               turns the selected rows into RREF.  Usually a no-op: k_sweep of
- *               the previous panel already ran this search on the first 512
+ *               the previous panel already ran this search on the first 1024
  *               active rows while the other SMs kept sweeping.
  *     k_apply   per strip: E = TB * Sel (reduced pivot rows), stores them at rows
  *               r..r+k-1 (physical swap with the displaced rows) and into the
- *               L2-resident staging tile ebuf[s] (64 x 128 B, indexed by column).
+ *               L2-resident staging tile ebuf[s] (64 x 64 B, indexed by column).
  *     k_sweep   persistent, 1 CTA / SM: TMA bulk-copies ebuf[s] into shared
- *               memory, builds nine Four-Russians tables (160 KiB of 128-byte
- *               lines), then streams every active row piece: 9 table XORs per
- *               16 B.  This is the HBM-bound kernel (2 * rows * 128 B per strip).
+ *               memory (one strip ahead), builds eight Four-Russians tables stored
+ *               as four line pairs (128 KiB), then streams every active row piece:
+ *               8 conflict-free table XORs per 16 B.  This is the HBM-bound kernel
+ *               (2 * rows * 64 B per strip).
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -486,24 +488,27 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
 /* ------------------------------------------------------------------------
  * k_sweep: the HBM-bound row-XOR sweep.
  *   rows [r1, m) x strips [s0, ns):  piece ^= XOR_g T_g[field g of (pc_cur[row] & pm)]
- * Persistent grid (1 CTA of 1024 threads per SM).  A work unit is 512 rows x one
- * strip (128 B per row, 64 KiB contiguous); units are dealt out contiguously in
- * strip-major order so a CTA rebuilds its tables only when it enters a new strip.
+ * Persistent grid (1 CTA of 1024 threads per SM).  A work unit is SWEEP_RU rows x one
+ * strip (64 KiB contiguous); units are dealt out contiguously in strip-major
+ * order so a CTA rebuilds its tables only when it enters a new strip.
  *
  * Four-Russians tables, laid out for conflict-free 128-bit lookups.  A lookup
  * wavefront is a quarter-warp (8 threads x 16 B).  In the first version (64-byte
- * strips and entries) it held 2 rows x 4 chunks and the two rows collided
- * whenever their indices had equal parity: ncu (profiles/r01a) showed 33% of all
- * shared wavefronts were such replays and the l1tex data pipe, not HBM, was the
- * limiter.  Now a strip piece and a table entry are both one 128-byte line and
- * the 8 threads of a quarter-warp are the 8 chunks of ONE row: they read one
- * whole line, all 32 banks, never a replay.  128-byte lines cost capacity, so
- * the 64 panel columns are split into eight 7-bit fields (128 lines each) plus
- * one 8-bit field (256 lines): 9 lookups per 16 B, all single-wavefront.
- *
- * Shared memory: TD[1280 lines][8] uint4 = 160 KiB + the mbarrier.  The build
- * scratch (the E tile filled by cp.async.bulk + mbarrier, partial tables P) and
- * the fused pivot search's scratch alias table space.
+ * strips, plain 64-byte entries) it held 2 rows x 4 chunks and the two rows
+ * collided whenever their indices had equal parity: ncu (profiles/r01a) showed 33%
+ * of all shared wavefronts were such replays and the l1tex data pipe, not HBM, was
+ * the limiter.  Two layouts avoid that:
+ *   SW = 16  a strip piece and a table entry are both one 128-byte line, the 8
+ *            threads of a quarter-warp are the 8 chunks of ONE row.  Whole lines
+ *            cost capacity: eight 7-bit fields + one 8-bit field, 9 lookups per
+ *            16 B, 160 KiB; build scratch and the fused pivot search's scratch
+ *            alias table space.
+ *   SW = 8   (default) entries are half lines stored in PAIRS of tables, the two
+ *            rows of a quarter-warp walk a pair in opposite order and therefore
+ *            always sit in opposite bank halves: eight full 8-bit fields, 8
+ *            lookups per 16 B, 128 KiB + 24 KiB of scratch behind the tables (E tile
+ *            and partial tables during a build, SelectSmem during the fused search).
+ * Both stay under the 164 KiB carve-out so the SM keeps its L1 for the loads in flight.
  * The CTA that updates the strip holding word w+1 also emits the dense copy of
  * that word column (pc_next) for the next panel's pivot search.
  * ---------------------------------------------------------------------- */
