@@ -104,9 +104,27 @@ def build(strip_words: int = 8, force: bool = False, asan: bool = False) -> Path
         os.symlink(ROOT / "include", inc_link)
     # storage behind the kernels' `extern __shared__` arrays
     (gen / "emu_shared.cpp").write_text(
+        "#include <stddef.h>\n"
         "namespace gf2b200 {\n"
         "alignas(128) unsigned char smem_raw[232 * 1024];\n"
         "alignas(128) unsigned long long xs[232 * 1024 / 8];\n"
+        "}\n"
+        "#ifdef __SANITIZE_ADDRESS__\n"
+        "#include <sanitizer/asan_interface.h>\n"
+        "#endif\n"
+        "/* a launch may touch only the dynamic shared memory it asked for */\n"
+        "extern \"C\" void emu_dynamic_smem(size_t bytes) {\n"
+        "#ifdef __SANITIZE_ADDRESS__\n"
+        "\tconst size_t cap = 232 * 1024;\n"
+        "\tbytes = (bytes + 7) & ~(size_t)7;\n"
+        "\tif (bytes > cap) bytes = cap;\n"
+        "\tASAN_UNPOISON_MEMORY_REGION(gf2b200::smem_raw, cap);\n"
+        "\tASAN_UNPOISON_MEMORY_REGION(gf2b200::xs, cap);\n"
+        "\tASAN_POISON_MEMORY_REGION(gf2b200::smem_raw + bytes, cap - bytes);\n"
+        "\tASAN_POISON_MEMORY_REGION((unsigned char *)gf2b200::xs + bytes, cap - bytes);\n"
+        "#else\n"
+        "\t(void)bytes;\n"
+        "#endif\n"
         "}\n")
     tmp = lib.with_suffix(f".tmp{os.getpid()}.so")
     cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-w", f"-DGF2_STRIP_WORDS={strip_words}",

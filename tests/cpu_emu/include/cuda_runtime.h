@@ -285,9 +285,11 @@ template <typename... P> struct Call {
 		std::apply(c->k, c->args);
 	}
 };
+extern "C" void emu_dynamic_smem(size_t bytes); /* ASan builds: poison what the launch did not ask for */
 template <typename... P, typename... A>
-static inline void launch(dim3 grid, dim3 block, size_t, cudaStream_t, void (*k)(P...), A &&...a) {
+static inline void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, void (*k)(P...), A &&...a) {
 	Call<P...> c{k, std::tuple<std::decay_t<P>...>(std::forward<A>(a)...)};
+	emu_dynamic_smem(smem);
 	run_grid(grid, block, &Call<P...>::thunk, &c);
 }
 } /* namespace emu */
