@@ -180,6 +180,17 @@ static int ctx_init(gf2b200_ctx **out, int device) {
 	e = cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM);
 	if (e == cudaSuccess)
 		e = cudaFuncSetAttribute(k_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	/* Tuning switch (off by default, not yet A/B-ed): GF2B200_CARVEOUT=<percent> asks for the
+	 * same shared-memory carve-out in the small per-panel kernels as k_sweep gets (164 of
+	 * 228 KiB = 72), so that the SMs are not re-partitioned three times per panel. */
+	if (const char *cv = getenv("GF2B200_CARVEOUT")) {
+		const int pct = atoi(cv);
+		if (e == cudaSuccess && pct > 0 && pct <= 100) {
+			e = cudaFuncSetAttribute(k_select, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+			if (e == cudaSuccess) e = cudaFuncSetAttribute(k_apply, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+			if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		}
+	}
 	if (e != cudaSuccess) {
 		int rc = fail(nullptr, GF2B200_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
 		free(c);
@@ -613,7 +624,11 @@ static int forward_single(gf2b200_system *sys, long long *launches) {
 		PanelDesc *pd = h.d_pd + (w & 1), *pdn = (w + 1 < nw && fused) ? h.d_pd + ((w + 1) & 1) : nullptr;
 		u64 colmask_next = ~0ULL;
 		if (w + 1 == nw - 1 && (M.n & 63)) colmask_next = (1ULL << (M.n & 63)) - 1;
-		k_select<<<1, SEL_THREADS, 0, st>>>(M, pc_cur, w, colmask, h.d_state, pd, h.d_hist_r, h.d_hist_pm);
+		/* SWEEP_TAIL_SELECT: the previous sweep's last CTA already settled this panel */
+		if (!(SWEEP_TAIL_SELECT && fused && w > 0)) {
+			k_select<<<1, SEL_THREADS, 0, st>>>(M, pc_cur, w, colmask, h.d_state, pd, h.d_hist_r, h.d_hist_pm);
+			(*launches)++;
+		}
 		int s0a = w >> SW_SHIFT;
 		k_apply<<<std::min(M.ns - s0a, apply_cap), APPLY_THREADS, 0, st>>>(M, pd, h.d_ebuf, s0a);
 		if (prof) CK(ctx, cudaEventRecord(sys->ev[4 + 2 * w], st));
@@ -621,7 +636,7 @@ static int forward_single(gf2b200_system *sys, long long *launches) {
 		                                                     (w + 1) >> SW_SHIFT,
 		                                                     pdn, h.d_state, h.d_hist_r, h.d_hist_pm, colmask_next);
 		if (prof) CK(ctx, cudaEventRecord(sys->ev[5 + 2 * w], st));
-		*launches += 3;
+		*launches += 2;
 	}
 	k_check<<<grid_for(M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(M, h.d_state);
 	(*launches)++;

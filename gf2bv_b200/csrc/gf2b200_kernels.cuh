@@ -94,6 +94,7 @@ struct SolverState {
 	long long r_loc; /* first active row of this shard (== r on a single GPU) */
 	int inconsistent;
 	int fault;       /* a peer-memory flag wait timed out */
+	unsigned sweep_done; /* SWEEP_TAIL_SELECT: CTAs of the running sweep that have finished */
 };
 
 __host__ __device__ __forceinline__ u64 mix64(u64 z) {
@@ -707,10 +708,18 @@ static_assert(SWEEP_THREADS == 8 * 32 * 4, "one partial-table item per thread; (
 #define SWEEP_SEL_PAD 6 /* units CTA 0 is spared to make room for the fused pivot search (2: 631, 4: 626, 6: 622 ms) */
 #endif
 
-__global__ void __launch_bounds__(SWEEP_THREADS, 1)
-k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
-        u64 *__restrict__ pc_next, const uint4 *__restrict__ ebuf, int w, int s0,
-        PanelDesc *pd_next, SolverState *st, long long *hist_r, u64 *hist_pm, u64 colmask_next) {
+#ifndef SWEEP_TAIL_SELECT
+/* 1: the last CTA of a sweep to finish runs the full pivot scan of the next panel
+ * when the fused search did not settle it, and the host stops launching k_select
+ * for panels > 0 (a no-op launch of ~2.3 us in almost every panel).  Off until it
+ * has been A/B-ed on a GPU; checked against the oracle on the emulated kernels. */
+#define SWEEP_TAIL_SELECT 0
+#endif
+
+__device__ __forceinline__ void
+sweep_body(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
+           u64 *__restrict__ pc_next, const uint4 *__restrict__ ebuf, int w, int s0,
+           PanelDesc *pd_next, SolverState *st, long long *hist_r, u64 *hist_pm, u64 colmask_next) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint4 *TD = reinterpret_cast<uint4 *>(smem_raw);
 #if SW == 16
@@ -901,6 +910,37 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
 			__syncthreads();
 		}
 	}
+}
+
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
+        u64 *__restrict__ pc_next, const uint4 *__restrict__ ebuf, int w, int s0,
+        PanelDesc *pd_next, SolverState *st, long long *hist_r, u64 *hist_pm, u64 colmask_next) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	sweep_body(M, pd, pc_cur, pc_next, ebuf, w, s0, pd_next, st, hist_r, hist_pm, colmask_next);
+#if SWEEP_TAIL_SELECT
+	if (!pd_next) return;
+	__shared__ int is_last;
+	__threadfence(); /* this CTA's pc_next words (and CTA 0's panel description) before its ticket */
+	__syncthreads();
+	if (threadIdx.x == 0) is_last = (atomicAdd(&st->sweep_done, 1u) == gridDim.x - 1);
+	__syncthreads();
+	if (!is_last) return;
+	if (threadIdx.x == 0) st->sweep_done = 0;
+	const int wn = w + 1;
+	if (*(volatile int *)&pd_next->valid == wn + 1) return;
+	/* the fused search saw too few rows (or none ran): scan every active row, as k_select would */
+#if SW == 16
+	SelectSmem &S = *reinterpret_cast<SelectSmem *>(smem_raw);
+#else
+	SelectSmem &S = *reinterpret_cast<SelectSmem *>(smem_raw + SWEEP_LINES * 128);
+#endif
+	const long long r = *(volatile long long *)&st->r;
+	select_init(S);
+	__syncthreads();
+	select_scan(S, pc_next, r, M.m, colmask_next);
+	if (threadIdx.x < 32) select_finalize(S, pc_next, wn, r, st, pd_next, hist_r, hist_pm);
+#endif
 }
 
 /* any active row (i >= rank) with b = 1 makes the system inconsistent

@@ -222,7 +222,7 @@ typedef struct emu_stream_ *cudaStream_t;
 struct emu_event_ { double t; };
 typedef emu_event_ *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 #define cudaStreamNonBlocking 1
 #define cudaEventDisableTiming 2
 #define cudaHostAllocPortable 1
