@@ -4,6 +4,8 @@
 # allocations are heap blocks and shared memory is static storage there, so an
 # out-of-bounds access of a kernel is reported like any heap/global overflow.
 # The GPU-side counterpart is scripts/sanitize.sh (compute-sanitizer memcheck/racecheck).
+# (UBSan: `python tests/cpu_emu/build_emu.py --ubsan`, LD_PRELOAD=$(gcc -print-file-name=libubsan.so);
+#  parity subset and tests/cpu_emu/fuzz_emu.py are clean under both.)
 #   scripts/emu_asan.sh [strip words: 8|16] [extra pytest args]
 set -eu
 SWORDS=${1:-8}; shift || true

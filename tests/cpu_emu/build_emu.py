@@ -3,7 +3,7 @@ CUDA sources (gf2bv_b200/csrc/*.cu, *.cuh) so the kernels' logic can be checked 
 a machine without a GPU.  See include/cuda_runtime.h for what the emulation is and
 is not.  The product (libgf2b200.so, nvcc, sm_100a) never contains any of this.
 
-    python tests/cpu_emu/build_emu.py [--strip-words 8|16] [--asan] -> prints the .so path
+    python tests/cpu_emu/build_emu.py [--strip-words 8|16] [--asan] [--ubsan] -> prints the .so path
 """
 from __future__ import annotations
 
@@ -82,11 +82,12 @@ def transform(text: str) -> str:
     return text
 
 
-def build(strip_words: int = 8, force: bool = False, asan: bool = False) -> Path:
+def build(strip_words: int = 8, force: bool = False, asan: bool = False, ubsan: bool = False) -> Path:
     """asan=True: AddressSanitizer build (device allocations are heap blocks, shared memory is
     static storage, so out-of-bounds kernel accesses are reported); load it with
-    LD_PRELOAD=$(gcc -print-file-name=libasan.so) -- see scripts/emu_asan.sh"""
-    out_dir = BUILD / (f"sw{strip_words}" + ("_asan" if asan else ""))
+    LD_PRELOAD=$(gcc -print-file-name=libasan.so) -- see scripts/emu_asan.sh.
+    ubsan=True: -fsanitize=undefined build (LD_PRELOAD libubsan.so)."""
+    out_dir = BUILD / (f"sw{strip_words}" + ("_asan" if asan else "") + ("_ubsan" if ubsan else ""))
     out_dir.mkdir(parents=True, exist_ok=True)
     lib = out_dir / "libgf2b200_emu.so"
     srcs = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [
@@ -129,6 +130,7 @@ def build(strip_words: int = 8, force: bool = False, asan: bool = False) -> Path
     tmp = lib.with_suffix(f".tmp{os.getpid()}.so")
     cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-w", f"-DGF2_STRIP_WORDS={strip_words}",
            *(["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []),
+           *(["-fsanitize=undefined", "-fno-sanitize=alignment", "-fno-sanitize-recover=undefined"] if ubsan else []),
            "-I", str(HERE / "include"), "-I", str(gen),
            "-o", str(tmp), str(gen / "gf2b200.cu.cpp"), str(gen / "emu_shared.cpp"), str(HERE / "emu_runtime.cpp"),
            "-ldl"]
@@ -142,5 +144,6 @@ if __name__ == "__main__":
     ap.add_argument("--strip-words", type=int, default=8)
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--asan", action="store_true")
+    ap.add_argument("--ubsan", action="store_true")
     a = ap.parse_args()
-    print(build(a.strip_words, a.force, a.asan))
+    print(build(a.strip_words, a.force, a.asan, a.ubsan))
