@@ -84,8 +84,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 #else
 /* tests/cpu_emu only: one thread runs everything, plain accesses are ordered */
-__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) { *(volatile unsigned *)p = v; }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) { return *(const volatile unsigned *)p; }
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ unsigned long long globaltimer_ns() { return (unsigned long long)(emu_now_ms() * 1e6); }
 #endif
 /* spin until *flag >= epoch (epochs only grow); gives up after ~4 s and reports a fault */

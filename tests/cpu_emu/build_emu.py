@@ -3,7 +3,7 @@ CUDA sources (gf2bv_b200/csrc/*.cu, *.cuh) so the kernels' logic can be checked 
 a machine without a GPU.  See include/cuda_runtime.h for what the emulation is and
 is not.  The product (libgf2b200.so, nvcc, sm_100a) never contains any of this.
 
-    python tests/cpu_emu/build_emu.py [--strip-words 8|16] [--asan] [--ubsan] -> prints the .so path
+    python tests/cpu_emu/build_emu.py [--strip-words 8|16] [--asan] [--ubsan] [--tsan] -> prints the .so path
 """
 from __future__ import annotations
 
@@ -82,12 +82,17 @@ def transform(text: str) -> str:
     return text
 
 
-def build(strip_words: int = 8, force: bool = False, asan: bool = False, ubsan: bool = False) -> Path:
+def build(strip_words: int = 8, force: bool = False, asan: bool = False, ubsan: bool = False,
+          tsan: bool = False) -> Path:
     """asan=True: AddressSanitizer build (device allocations are heap blocks, shared memory is
     static storage, so out-of-bounds kernel accesses are reported); load it with
     LD_PRELOAD=$(gcc -print-file-name=libasan.so) -- see scripts/emu_asan.sh.
-    ubsan=True: -fsanitize=undefined build (LD_PRELOAD libubsan.so)."""
-    out_dir = BUILD / (f"sw{strip_words}" + ("_asan" if asan else "") + ("_ubsan" if ubsan else ""))
+    ubsan=True: -fsanitize=undefined build (LD_PRELOAD libubsan.so).
+    tsan=True: ThreadSanitizer build -- GPU threads are TSan fibers and only the GPU's own
+    synchronisation orders them, so races between GPU threads on shared/global memory are
+    reported (a CPU-side racecheck; LD_PRELOAD libtsan.so, see scripts/emu_tsan.sh)."""
+    out_dir = BUILD / (f"sw{strip_words}" + ("_asan" if asan else "") + ("_ubsan" if ubsan else "") +
+                       ("_tsan" if tsan else ""))
     out_dir.mkdir(parents=True, exist_ok=True)
     lib = out_dir / "libgf2b200_emu.so"
     srcs = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [
@@ -128,13 +133,16 @@ def build(strip_words: int = 8, force: bool = False, asan: bool = False, ubsan: 
         "#endif\n"
         "}\n")
     tmp = lib.with_suffix(f".tmp{os.getpid()}.so")
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-w", f"-DGF2_STRIP_WORDS={strip_words}",
-           *(["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []),
-           *(["-fsanitize=undefined", "-fno-sanitize=alignment", "-fno-sanitize-recover=undefined"] if ubsan else []),
-           "-I", str(HERE / "include"), "-I", str(gen),
-           "-o", str(tmp), str(gen / "gf2b200.cu.cpp"), str(gen / "emu_shared.cpp"), str(HERE / "emu_runtime.cpp"),
-           "-ldl"]
-    subprocess.check_call(cmd)
+    san = [*(["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []),
+           *(["-fsanitize=undefined", "-fno-sanitize=alignment", "-fno-sanitize-recover=undefined"] if ubsan else [])]
+    base = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-w", f"-DGF2_STRIP_WORDS={strip_words}",
+            "-I", str(HERE / "include"), "-I", str(gen)]
+    # the scheduler is never TSan-instrumented: its bookkeeping is not GPU memory
+    rt_obj = out_dir / "emu_runtime.o"
+    subprocess.check_call([*base, *san, *(["-DEMU_TSAN"] if tsan else []), "-c", str(HERE / "emu_runtime.cpp"),
+                           "-o", str(rt_obj)])
+    subprocess.check_call([*base, *san, *(["-fsanitize=thread"] if tsan else []), "-shared", "-o", str(tmp),
+                           str(gen / "gf2b200.cu.cpp"), str(gen / "emu_shared.cpp"), str(rt_obj), "-ldl"])
     os.replace(tmp, lib)
     return lib
 
@@ -145,5 +153,6 @@ if __name__ == "__main__":
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--asan", action="store_true")
     ap.add_argument("--ubsan", action="store_true")
+    ap.add_argument("--tsan", action="store_true")
     a = ap.parse_args()
-    print(build(a.strip_words, a.force, a.asan, a.ubsan))
+    print(build(a.strip_words, a.force, a.asan, a.ubsan, a.tsan))

@@ -31,7 +31,32 @@ __asm__(
     "  ret\n"
     ".size emu_switch,.-emu_switch\n");
 
-void yield_to_scheduler() { emu_switch(&cur->sp, sched_sp); }
+/* EMU_TSAN (build_emu.py --tsan): this file itself is compiled WITHOUT -fsanitize=thread --
+ * the scheduler's bookkeeping is not GPU memory -- and only drives TSan's fiber API */
+#ifdef EMU_TSAN
+extern "C" {
+void *__tsan_get_current_fiber(void);
+void *__tsan_create_fiber(unsigned flags);
+void __tsan_switch_to_fiber(void *fiber, unsigned flags);
+void __tsan_acquire(void *addr);
+void __tsan_release(void *addr);
+}
+static void *sched_tsan = nullptr;
+static std::vector<void *> tsan_fibers;
+static int launch_obj; /* kernel boundary: host -> every GPU thread -> host */
+#define TSAN_TO(f) __tsan_switch_to_fiber((f), 1 /* no implied synchronisation */)
+#undef EMU_ACQUIRE
+#undef EMU_RELEASE
+#define EMU_ACQUIRE(p) __tsan_acquire((void *)(p))
+#define EMU_RELEASE(p) __tsan_release((void *)(p))
+#else
+#define TSAN_TO(f) ((void)0)
+#endif
+
+void yield_to_scheduler() {
+	TSAN_TO(sched_tsan);
+	emu_switch(&cur->sp, sched_sp);
+}
 
 void warp_complete_if_ready(Warp &W) {
 	if (W.departing || !W.arrived || W.arrived != W.live) return;
@@ -42,7 +67,13 @@ void warp_complete_if_ready(Warp &W) {
 }
 
 static void fiber_main() {
+#ifdef EMU_TSAN
+	EMU_ACQUIRE(&launch_obj);
+#endif
 	g_thunk(g_arg);
+#ifdef EMU_TSAN
+	EMU_RELEASE(&launch_obj);
+#endif
 	Fiber *f = cur;
 	f->done = 1;
 	cta.alive--;
@@ -53,6 +84,7 @@ static void fiber_main() {
 		cta.bar_arrived = 0;
 		cta.bar_gen++;
 	}
+	TSAN_TO(sched_tsan);
 	emu_switch(&f->sp, sched_sp);
 	abort(); /* a finished fiber is never resumed */
 }
@@ -63,7 +95,7 @@ static bool runnable(const Fiber &f) {
 	case W_BARRIER: return f.bar_gen != cta.bar_gen;
 	case W_WARP_ENTER: return cta.w[f.warp].departing == 0;
 	case W_WARP_RESULT: return (cta.w[f.warp].departing >> f.lane) & 1;
-	case W_WORD: return (*f.word & 1) != f.word_val;
+	case W_WORD: return (__atomic_load_n((const unsigned long long *)f.word, __ATOMIC_ACQUIRE) & 1) != f.word_val;
 	}
 	return true;
 }
@@ -82,6 +114,10 @@ void run_grid(dim3 grid, dim3 block, void (*thunk)(void *), void *arg) {
 	g_blockDim = block;
 	cta.f.resize(nt);
 	cta.w.resize((nt + 31) / 32);
+#ifdef EMU_TSAN
+	sched_tsan = __tsan_get_current_fiber();
+	EMU_RELEASE(&launch_obj);
+#endif
 	for (unsigned bx = 0; bx < grid.x; bx++) {
 		g_blockIdx = dim3(bx);
 		cta.alive = (int)nt;
@@ -103,6 +139,10 @@ void run_grid(dim3 grid, dim3 block, void (*thunk)(void *), void *arg) {
 			*--sp = (void *)fiber_main;
 			for (int i = 0; i < 6; i++) *--sp = nullptr;
 			f.sp = sp;
+#ifdef EMU_TSAN
+			if (t >= tsan_fibers.size()) tsan_fibers.push_back(__tsan_create_fiber(0));
+			f.tsan = tsan_fibers[t];
+#endif
 		}
 		int remaining = (int)nt;
 		while (remaining > 0) {
@@ -112,6 +152,7 @@ void run_grid(dim3 grid, dim3 block, void (*thunk)(void *), void *arg) {
 				if (f.done || !runnable(f)) continue;
 				f.wait = W_NONE;
 				cur = &f;
+				TSAN_TO(f.tsan);
 				emu_switch(&sched_sp, f.sp);
 				progress = true;
 				if (f.done) remaining--;
@@ -122,6 +163,9 @@ void run_grid(dim3 grid, dim3 block, void (*thunk)(void *), void *arg) {
 			}
 		}
 	}
+#ifdef EMU_TSAN
+	EMU_ACQUIRE(&launch_obj);
+#endif
 	cur = nullptr;
 }
 

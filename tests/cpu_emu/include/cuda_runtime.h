@@ -50,6 +50,28 @@ struct dim3 {
 	dim3(long long x_) : x((unsigned)x_), y(1), z(1) {}
 };
 
+/* ThreadSanitizer build (build_emu.py --tsan): every GPU thread is a TSan fiber and only
+ * the GPU's own synchronisation (barriers, warp collectives, mbarriers, atomics, kernel
+ * boundaries) creates happens-before edges, so TSan reports shared/global-memory races
+ * between GPU threads -- a CPU-side racecheck. */
+#ifdef __SANITIZE_THREAD__
+extern "C" {
+void *__tsan_get_current_fiber(void);
+void *__tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void *fiber);
+void __tsan_switch_to_fiber(void *fiber, unsigned flags);
+void __tsan_acquire(void *addr);
+void __tsan_release(void *addr);
+}
+#define EMU_ACQUIRE(p) __tsan_acquire((void *)(p))
+#define EMU_RELEASE(p) __tsan_release((void *)(p))
+#define EMU_INTERNAL __attribute__((no_sanitize("thread"))) /* the emulator's own bookkeeping is not GPU memory */
+#else
+#define EMU_ACQUIRE(p) ((void)0)
+#define EMU_RELEASE(p) ((void)0)
+#define EMU_INTERNAL
+#endif
+
 namespace emu {
 
 enum WaitKind { W_NONE = 0, W_BARRIER, W_WARP_ENTER, W_WARP_RESULT, W_WORD };
@@ -71,6 +93,7 @@ struct Fiber {
 	unsigned long long word_val;
 	dim3 tid;
 	int lane, warp;
+	void *tsan; /* TSan fiber handle (ThreadSanitizer builds) */
 };
 
 struct Cta {
@@ -90,20 +113,22 @@ void yield_to_scheduler();
 void run_grid(dim3 grid, dim3 block, void (*thunk)(void *), void *arg);
 void warp_complete_if_ready(Warp &W);
 
-static inline void block_on(int kind) {
+EMU_INTERNAL static inline void block_on(int kind) {
 	cur->wait = kind;
 	yield_to_scheduler();
 }
 
 /* every live lane deposits v; returns the snapshot of all lanes (0 for dead lanes) */
-static inline const unsigned long long *warp_exchange(unsigned long long v, unsigned *mask_out = nullptr) {
+EMU_INTERNAL static inline const unsigned long long *warp_exchange(unsigned long long v, unsigned *mask_out = nullptr) {
 	Warp &W = cta.w[cur->warp];
 	const unsigned bit = 1u << cur->lane;
 	while (W.departing) block_on(W_WARP_ENTER);
 	W.vals[cur->lane] = v;
 	W.arrived |= bit;
+	EMU_RELEASE(&W);
 	warp_complete_if_ready(W);
 	while (!(W.departing & bit)) block_on(W_WARP_RESULT);
+	EMU_ACQUIRE(&W);
 	static thread_local unsigned long long out[32];
 	memcpy(out, W.snap, sizeof out);
 	if (mask_out) *mask_out = W.snap_mask;
@@ -111,50 +136,58 @@ static inline const unsigned long long *warp_exchange(unsigned long long v, unsi
 	return out;
 }
 
+EMU_INTERNAL static inline const dim3 &self_tid() { return cur->tid; }
+EMU_INTERNAL static inline const dim3 &self_bid() { return g_blockIdx; }
+EMU_INTERNAL static inline const dim3 &self_bdim() { return g_blockDim; }
+EMU_INTERNAL static inline const dim3 &self_gdim() { return g_gridDim; }
+
 } /* namespace emu */
 
-#define threadIdx (emu::cur->tid)
-#define blockIdx (emu::g_blockIdx)
-#define blockDim (emu::g_blockDim)
-#define gridDim (emu::g_gridDim)
+#define threadIdx (emu::self_tid())
+#define blockIdx (emu::self_bid())
+#define blockDim (emu::self_bdim())
+#define gridDim (emu::self_gdim())
 
 /* ---- device intrinsics ---------------------------------------------------- */
-static inline void __syncthreads() {
+EMU_INTERNAL static inline void __syncthreads() {
 	emu::Cta &C = emu::cta;
+	EMU_RELEASE(&C.bar_gen);
 	C.bar_arrived++;
 	if (C.bar_arrived == C.alive) {
 		C.bar_arrived = 0;
 		C.bar_gen++;
+		EMU_ACQUIRE(&C.bar_gen);
 		return;
 	}
 	emu::cur->bar_gen = C.bar_gen;
 	while (emu::cur->bar_gen == C.bar_gen) emu::block_on(emu::W_BARRIER);
+	EMU_ACQUIRE(&C.bar_gen);
 }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_exchange(0); }
-static inline unsigned __ballot_sync(unsigned, int pred) {
+EMU_INTERNAL static inline unsigned __ballot_sync(unsigned, int pred) {
 	const unsigned long long *s = emu::warp_exchange(pred ? 1 : 0);
 	unsigned r = 0;
 	for (int i = 0; i < 32; i++) r |= (unsigned)(s[i] & 1) << i;
 	return r;
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
-static inline int __all_sync(unsigned m, int pred) {
+EMU_INTERNAL static inline int __all_sync(unsigned m, int pred) {
 	unsigned live;
 	const unsigned long long *s = emu::warp_exchange(pred ? 1 : 0, &live);
 	for (int i = 0; i < 32; i++)
 		if (((live >> i) & 1) && !s[i]) return 0;
 	return 1;
 }
-static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return (unsigned)emu::warp_exchange(v)[src & 31]; }
-static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu::warp_exchange((unsigned)v)[src & 31]; }
-static inline unsigned __reduce_xor_sync(unsigned, unsigned v) {
+EMU_INTERNAL static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return (unsigned)emu::warp_exchange(v)[src & 31]; }
+EMU_INTERNAL static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu::warp_exchange((unsigned)v)[src & 31]; }
+EMU_INTERNAL static inline unsigned __reduce_xor_sync(unsigned, unsigned v) {
 	const unsigned long long *s = emu::warp_exchange(v);
 	unsigned r = 0;
 	for (int i = 0; i < 32; i++) r ^= (unsigned)s[i];
 	return r;
 }
 static inline int __reduce_xor_sync(unsigned m, int v) { return (int)__reduce_xor_sync(m, (unsigned)v); }
-static inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+EMU_INTERNAL static inline unsigned __reduce_or_sync(unsigned, unsigned v) {
 	const unsigned long long *s = emu::warp_exchange(v);
 	unsigned r = 0;
 	for (int i = 0; i < 32; i++) r |= (unsigned)s[i];
@@ -186,12 +219,12 @@ static inline void __threadfence() {}
 static inline void __threadfence_system() {}
 static inline void __threadfence_block() {}
 static inline void __nanosleep(unsigned) {}
-static inline int atomicOr(int *p, int v) { int o = *p; *p = o | v; return o; }
-static inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
-static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o | v; return o; }
-static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
-static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
-static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+static inline int atomicOr(int *p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
@@ -205,15 +238,19 @@ static inline long long max(int a, long long b) { return a > b ? a : b; }
 
 /* mbarrier + bulk copy stand-ins used by the GF2_EMU branches of the kernels:
  * the barrier word's bit 0 is the phase that completes next */
-static inline void emu_mbar_init(void *bar) { *(volatile unsigned long long *)bar = 0; }
-static inline void emu_mbar_complete(void *bar) { *(volatile unsigned long long *)bar ^= 1; }
-static inline void emu_mbar_wait(void *bar, unsigned phase) {
+static inline void emu_mbar_init(void *bar) { __atomic_store_n((unsigned long long *)bar, 0ULL, __ATOMIC_RELEASE); }
+static inline void emu_mbar_complete(void *bar) {
+	EMU_RELEASE(bar);
+	__atomic_fetch_xor((unsigned long long *)bar, 1ULL, __ATOMIC_RELEASE);
+}
+EMU_INTERNAL static inline void emu_mbar_wait(void *bar, unsigned phase) {
 	volatile unsigned long long *b = (volatile unsigned long long *)bar;
-	while ((*b & 1) == phase) {
+	while ((__atomic_load_n((unsigned long long *)bar, __ATOMIC_ACQUIRE) & 1) == phase) {
 		emu::cur->word = b;
 		emu::cur->word_val = phase;
 		emu::block_on(emu::W_WORD);
 	}
+	EMU_ACQUIRE(bar);
 }
 
 /* ---- runtime API ------------------------------------------------------------ */
