@@ -596,8 +596,7 @@ __device__ __forceinline__ void mbar_init_fence() {}
 __device__ __forceinline__ void mbar_expect_tx(void *, unsigned) {}
 __device__ __forceinline__ void mbar_wait(void *bar, unsigned phase) { emu_mbar_wait(bar, phase); }
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar) {
-	memcpy(dst, src, bytes);
-	emu_mbar_complete(bar);
+	emu_bulk_copy(dst, src, bytes, bar);
 }
 #endif
 

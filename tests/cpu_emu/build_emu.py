@@ -3,7 +3,7 @@ CUDA sources (gf2bv_b200/csrc/*.cu, *.cuh) so the kernels' logic can be checked 
 a machine without a GPU.  See include/cuda_runtime.h for what the emulation is and
 is not.  The product (libgf2b200.so, nvcc, sm_100a) never contains any of this.
 
-    python tests/cpu_emu/build_emu.py [--strip-words 8|16] [--asan] [--ubsan] [--tsan] -> prints the .so path
+    python tests/cpu_emu/build_emu.py [--strip-words 8|16] [--asan] [--ubsan] [--tsan] [--racecheck] -> prints the .so path
 """
 from __future__ import annotations
 
@@ -83,21 +83,24 @@ def transform(text: str) -> str:
 
 
 def build(strip_words: int = 8, force: bool = False, asan: bool = False, ubsan: bool = False,
-          tsan: bool = False) -> Path:
+          tsan: bool = False, racecheck: bool = False) -> Path:
     """asan=True: AddressSanitizer build (device allocations are heap blocks, shared memory is
     static storage, so out-of-bounds kernel accesses are reported); load it with
     LD_PRELOAD=$(gcc -print-file-name=libasan.so) -- see scripts/emu_asan.sh.
     ubsan=True: -fsanitize=undefined build (LD_PRELOAD libubsan.so).
     tsan=True: ThreadSanitizer build -- GPU threads are TSan fibers and only the GPU's own
     synchronisation orders them, so races between GPU threads on shared/global memory are
-    reported (a CPU-side racecheck; LD_PRELOAD libtsan.so, see scripts/emu_tsan.sh)."""
+    reported -- only for CTAs of up to ~250 threads (TSan's slot limit); LD_PRELOAD libtsan.so.
+    racecheck=True: the same compiler hooks feed emu_racecheck.cpp instead of libtsan: a
+    hazard checker in the spirit of compute-sanitizer racecheck that knows the GPU's
+    synchronisation and handles full-size CTAs (no preload needed)."""
     out_dir = BUILD / (f"sw{strip_words}" + ("_asan" if asan else "") + ("_ubsan" if ubsan else "") +
-                       ("_tsan" if tsan else ""))
+                       ("_tsan" if tsan else "") + ("_racecheck" if racecheck else ""))
     out_dir.mkdir(parents=True, exist_ok=True)
     lib = out_dir / "libgf2b200_emu.so"
     srcs = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [
         ROOT / "include" / "gf2b200.h", HERE / "include" / "cuda_runtime.h", HERE / "include" / "nccl.h",
-        HERE / "emu_runtime.cpp", Path(__file__)]
+        HERE / "emu_runtime.cpp", HERE / "emu_racecheck.cpp", Path(__file__)]
     if not force and lib.exists() and all(lib.stat().st_mtime >= s.stat().st_mtime for s in srcs):
         return lib
     # mirror the source tree's relative layout: gf2b200.cu includes "../../include/gf2b200.h"
@@ -139,10 +142,20 @@ def build(strip_words: int = 8, force: bool = False, asan: bool = False, ubsan: 
             "-I", str(HERE / "include"), "-I", str(gen)]
     # the scheduler is never TSan-instrumented: its bookkeeping is not GPU memory
     rt_obj = out_dir / "emu_runtime.o"
-    subprocess.check_call([*base, *san, *(["-DEMU_TSAN"] if tsan else []), "-c", str(HERE / "emu_runtime.cpp"),
-                           "-o", str(rt_obj)])
-    subprocess.check_call([*base, *san, *(["-fsanitize=thread"] if tsan else []), "-shared", "-o", str(tmp),
-                           str(gen / "gf2b200.cu.cpp"), str(gen / "emu_shared.cpp"), str(rt_obj), "-ldl"])
+    rt_def = ["-DEMU_TSAN"] if tsan else ["-DEMU_RACECHECK"] if racecheck else []
+    subprocess.check_call([*base, *san, *rt_def, "-c", str(HERE / "emu_runtime.cpp"), "-o", str(rt_obj)])
+    objs = [str(rt_obj)]
+    if racecheck:
+        # kernels compiled with TSan's hooks, linked against OUR implementation of them (no libtsan)
+        k_obj, s_obj, rc_obj = out_dir / "kernels.o", out_dir / "emu_shared.o", out_dir / "emu_racecheck.o"
+        subprocess.check_call([*base, "-fsanitize=thread", "-DEMU_RACECHECK", "-c", str(gen / "gf2b200.cu.cpp"),
+                               "-o", str(k_obj)])
+        subprocess.check_call([*base, "-c", str(gen / "emu_shared.cpp"), "-o", str(s_obj)])
+        subprocess.check_call([*base, "-DEMU_RACECHECK", "-c", str(HERE / "emu_racecheck.cpp"), "-o", str(rc_obj)])
+        subprocess.check_call(["g++", "-shared", "-o", str(tmp), str(k_obj), str(s_obj), str(rc_obj), *objs, "-ldl"])
+    else:
+        subprocess.check_call([*base, *san, *(["-fsanitize=thread"] if tsan else []), "-shared", "-o", str(tmp),
+                               str(gen / "gf2b200.cu.cpp"), str(gen / "emu_shared.cpp"), *objs, "-ldl"])
     os.replace(tmp, lib)
     return lib
 
@@ -154,5 +167,6 @@ if __name__ == "__main__":
     ap.add_argument("--asan", action="store_true")
     ap.add_argument("--ubsan", action="store_true")
     ap.add_argument("--tsan", action="store_true")
+    ap.add_argument("--racecheck", action="store_true")
     a = ap.parse_args()
-    print(build(a.strip_words, a.force, a.asan, a.ubsan, a.tsan))
+    print(build(a.strip_words, a.force, a.asan, a.ubsan, a.tsan, a.racecheck))

@@ -5,6 +5,10 @@
 #include <cuda_runtime.h>
 #include <sys/mman.h>
 
+#ifdef EMU_RACECHECK
+extern "C" void emu_racecheck_launch(void);
+#endif
+
 namespace emu {
 
 Fiber *cur = nullptr;
@@ -15,6 +19,10 @@ void *sched_sp = nullptr;
 static const size_t STACK = 64 * 1024;
 static char *stacks = nullptr;
 static size_t n_stacks = 0;
+/* for the hazard checker (emu_racecheck.cpp) */
+char *stacks_base = nullptr;
+size_t stacks_bytes = 0;
+unsigned launch_seq = 0;
 static void (*g_thunk)(void *) = nullptr;
 static void *g_arg = nullptr;
 
@@ -60,6 +68,7 @@ void yield_to_scheduler() {
 
 void warp_complete_if_ready(Warp &W) {
 	if (W.departing || !W.arrived || W.arrived != W.live) return;
+	W.gen++;
 	for (int i = 0; i < 32; i++) W.snap[i] = ((W.arrived >> i) & 1) ? W.vals[i] : 0;
 	W.snap_mask = W.arrived;
 	W.departing = W.arrived;
@@ -107,7 +116,13 @@ void run_grid(dim3 grid, dim3 block, void (*thunk)(void *), void *arg) {
 		stacks = (char *)mmap(nullptr, nt * STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
 		if (stacks == MAP_FAILED) abort();
 		n_stacks = nt;
+		stacks_base = stacks;
+		stacks_bytes = nt * STACK;
 	}
+	launch_seq++;
+#ifdef EMU_RACECHECK
+	emu_racecheck_launch();
+#endif
 	g_thunk = thunk;
 	g_arg = arg;
 	g_gridDim = grid;
@@ -123,11 +138,13 @@ void run_grid(dim3 grid, dim3 block, void (*thunk)(void *), void *arg) {
 		cta.alive = (int)nt;
 		cta.bar_arrived = 0;
 		cta.bar_gen = 0;
+		cta.tma_count = 0;
 		for (Warp &W : cta.w) memset(&W, 0, sizeof W);
 		for (size_t t = 0; t < nt; t++) {
 			Fiber &f = cta.f[t];
 			f.done = 0;
 			f.wait = W_NONE;
+			f.tma_seen = 0;
 			f.tid = dim3((unsigned)(t % block.x), (unsigned)(t / block.x));
 			f.lane = (int)(t & 31);
 			f.warp = (int)(t >> 5);

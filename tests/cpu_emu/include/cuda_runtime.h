@@ -78,6 +78,7 @@ enum WaitKind { W_NONE = 0, W_BARRIER, W_WARP_ENTER, W_WARP_RESULT, W_WORD };
 
 struct Warp {
 	unsigned long long vals[32], snap[32];
+	unsigned gen;       /* completed collectives (racecheck: orders accesses inside the warp) */
 	unsigned live;      /* lanes that have not exited */
 	unsigned arrived;   /* lanes waiting in the current collective */
 	unsigned departing; /* lanes that still have to read snap */
@@ -94,6 +95,7 @@ struct Fiber {
 	dim3 tid;
 	int lane, warp;
 	void *tsan; /* TSan fiber handle (ThreadSanitizer builds) */
+	unsigned tma_seen; /* racecheck: bulk copies of this CTA whose mbarrier phase this thread has waited for */
 };
 
 struct Cta {
@@ -101,6 +103,7 @@ struct Cta {
 	std::vector<Warp> w;
 	int alive, bar_arrived;
 	unsigned bar_gen;
+	unsigned tma_count; /* bulk copies issued in this CTA so far */
 };
 
 extern Fiber *cur;
@@ -243,6 +246,16 @@ static inline void emu_mbar_complete(void *bar) {
 	EMU_RELEASE(bar);
 	__atomic_fetch_xor((unsigned long long *)bar, 1ULL, __ATOMIC_RELEASE);
 }
+extern "C" void emu_racecheck_bulk_write(void *dst, size_t bytes, unsigned seq); /* --racecheck builds */
+/* the bulk copy (TMA stand-in): done at once, completes the barrier's current phase */
+EMU_INTERNAL static inline void emu_bulk_copy(void *dst, const void *src, unsigned bytes, void *bar) {
+	memcpy(dst, src, bytes);
+	emu::cta.tma_count++;
+#ifdef EMU_RACECHECK
+	emu_racecheck_bulk_write(dst, bytes, emu::cta.tma_count);
+#endif
+	emu_mbar_complete(bar);
+}
 EMU_INTERNAL static inline void emu_mbar_wait(void *bar, unsigned phase) {
 	volatile unsigned long long *b = (volatile unsigned long long *)bar;
 	while ((__atomic_load_n((unsigned long long *)bar, __ATOMIC_ACQUIRE) & 1) == phase) {
@@ -251,6 +264,7 @@ EMU_INTERNAL static inline void emu_mbar_wait(void *bar, unsigned phase) {
 		emu::block_on(emu::W_WORD);
 	}
 	EMU_ACQUIRE(bar);
+	emu::cur->tma_seen = emu::cta.tma_count;
 }
 
 /* ---- runtime API ------------------------------------------------------------ */
