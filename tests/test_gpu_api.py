@@ -166,6 +166,57 @@ def test_quadratic_system_small():
     assert q.solve_one(zeros) == sols[0]
 
 
+def _lfsr_step(state, nbits, tapmask):
+    """One step of a Fibonacci LFSR on an int or a BitVec: shift right, feedback into the top bit."""
+    if isinstance(state, int):
+        fb = bin(state & tapmask).count("1") & 1
+        return (state >> 1) | (fb << (nbits - 1))
+    fb = (state & tapmask).sum()
+    return (state >> 1) ^ (fb.broadcast(0, nbits) & (1 << (nbits - 1)))
+
+
+@pytest.mark.parametrize("nbits,nout,seed,nullity", [(24, 600, 4, 2), (24, 600, 1, 26), (40, 1700, 3, 3),
+                                                     pytest.param(128, 9000, 1, 0, id="full128")])
+def test_filter_generator_by_linearisation(nbits, nout, seed, nullity):
+    """The workload class of the reference's examples/nlfsr.py (QuadraticSystem feeding the
+    solve path with n + n(n-1)/2 columns; 128 bits -> 8256 columns as in nlfsr.py:45): a
+    quadratic filter on an LFSR state, recovered through solve_all / solve_one.  State, taps
+    and filter are seeded, so the answer is pinned; the raw solution space must equal the
+    oracle's (origin, kernel basis values and order)."""
+    rnd = random.Random(seed)
+    tapmask = rnd.getrandbits(nbits) | 1 | (1 << (nbits - 1))
+    pick = rnd.sample(range(nbits), 4)
+    init = rnd.getrandbits(nbits) | 1
+    q = gf2bv.QuadraticSystem([nbits])
+    (x,) = q.gens()
+    st, sym, zeros, outs = init, x, [], []
+    for _ in range(nout):
+        st, sym = _lfsr_step(st, nbits, tapmask), _lfsr_step(sym, nbits, tapmask)
+        a, b, c, d = [(st >> i) & 1 for i in pick]
+        A, B, C, D = [sym[i] for i in pick]
+        outs.append((a & b) ^ (c & d) ^ a ^ c)
+        zeros.append(q.mul_bit(A, B) ^ q.mul_bit(C, D) ^ A ^ C ^ outs[-1])
+    cols = nbits + nbits * (nbits - 1) // 2
+    eqs = q.get_eqs(zeros)
+    eqs = eqs + [0] * max(0, cols - len(eqs))
+    got, want = _internal.m4ri_solve(eqs, cols, 1), oracle.m4ri_solve(eqs, cols, 1)
+    assert got.dimension == want.dimension == nullity
+    assert got.origin == want.origin and tuple(got.basis) == tuple(want.basis)
+    if nullity > 16:
+        with pytest.raises(gf2bv.DimensionTooLargeError) as ei:
+            list(q.solve_all(zeros))
+        assert ei.value.space.dimension == nullity
+        return
+    sols = list(q.solve_all(zeros))
+    assert (init,) in sols and q.solve_one(zeros) == sols[0]
+    for (sol,) in sols:  # every solution that survives the monomial filter reproduces the outputs
+        st = sol
+        for o in outs[:300]:
+            st = _lfsr_step(st, nbits, tapmask)
+            a, b, c, d = [(st >> i) & 1 for i in pick]
+            assert ((a & b) ^ (c & d) ^ a ^ c) == o
+
+
 def test_concurrent_calls_from_threads():
     # the reference releases the GIL around the solve (_internal.c:429); concurrent callers are legal
     rnd = random.Random(3)
