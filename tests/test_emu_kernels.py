@@ -4,8 +4,8 @@ No GPU here, so this is the only tier that can notice a logic error in the kerne
 (table layouts, pivot bookkeeping, shard exchange order) before the GPU box does:
 tests/cpu_emu/build_emu.py compiles gf2bv_b200/csrc/*.cu(h) with g++ against a
 stand-in for the CUDA runtime (threads of a CTA = fibers) and the GPU parity tests
-(tests/test_gpu_solver.py, tests/test_gpu_sharded.py -- same cases, same oracle
-checks) are run in a subprocess whose GF2B200_LIB points at that build.
+(tests/test_gpu_solver.py, tests/test_gpu_sharded.py, tests/test_gpu_api.py -- same
+cases, same oracle checks) are run in a subprocess whose GF2B200_LIB points at that build.
 
 This is test infrastructure: the emulated library lives under tests/cpu_emu/_build,
 is never built by ``__graft_entry__.build()`` and never loaded by the package on its
@@ -26,7 +26,7 @@ sys.path.insert(0, str(ROOT / "tests" / "cpu_emu"))
 
 # the heavy cases stay on the GPU; everything else is the GPU suite verbatim
 SUBSET = ("not 32768 and not mt19937 and not 8192 and not 1025-3000 and not 2000-1500 and not 4099 "
-          "and not 5000 and not 4096 and not 0.001 and not 2100 and not bignull")
+          "and not 5000 and not 4096 and not 0.001 and not 2100 and not bignull and not full128")
 
 
 @pytest.fixture(scope="module")
@@ -38,7 +38,8 @@ def emu_runs():
         lib = build_emu.build(sw)
         env = dict(os.environ, GF2B200_LIB=str(lib), GF2_EMU_SMS="3")
         procs[sw] = subprocess.Popen(
-            [sys.executable, "-m", "pytest", "tests/test_gpu_solver.py", "tests/test_gpu_sharded.py", "-m", "gpu",
+            [sys.executable, "-m", "pytest", "tests/test_gpu_solver.py", "tests/test_gpu_sharded.py",
+             "tests/test_gpu_api.py", "-m", "gpu",
              "-x", "-q", "-p", "no:cacheprovider", "-k", SUBSET],
             cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     out = {}
