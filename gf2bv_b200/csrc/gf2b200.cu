@@ -900,21 +900,23 @@ extern "C" int gf2b200_system_result(gf2b200_system *sys, int mode, gf2b200_resu
 			long long launches = 0;
 			double xbytes = 0;
 			int rc = GF2B200_OK;
-			for (long long i = 0; i < d && !rc; i++) {
+			cudaError_t e = cudaSuccess;
+			for (long long i = 0; i < d && !rc && e == cudaSuccess; i++) {
 				rc = backward(sys, &launches, &xbytes, sigma[r + i]);
 				if (!rc)
-					CK(ctx, cudaMemcpyAsync(out->basis + i * nw, h.d_x, (size_t)nw * 8, cudaMemcpyDeviceToHost,
-					                        ctx->stream));
+					e = cudaMemcpyAsync(out->basis + i * nw, h.d_x, (size_t)nw * 8, cudaMemcpyDeviceToHost,
+					                    ctx->stream);
 			}
 			for (Shard &sh : sys->sh) {
 				static const u64 one = 1;
-				CK(ctx, cudaMemcpyAsync(sh.d_x, out->origin, (size_t)nw * 8, cudaMemcpyHostToDevice, ctx->stream));
-				CK(ctx, cudaMemcpyAsync(sh.d_x + nw, &one, 8, cudaMemcpyHostToDevice, ctx->stream));
+				if (e == cudaSuccess)
+					e = cudaMemcpyAsync(sh.d_x, out->origin, (size_t)nw * 8, cudaMemcpyHostToDevice, ctx->stream);
+				if (e == cudaSuccess) e = cudaMemcpyAsync(sh.d_x + nw, &one, 8, cudaMemcpyHostToDevice, ctx->stream);
 			}
-			CK(ctx, cudaStreamSynchronize(ctx->stream));
-			if (rc) {
+			if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+			if (rc || e != cudaSuccess) {
 				gf2b200_result_free(out);
-				return rc;
+				return rc ? rc : fail(ctx, GF2B200_ECUDA, "kernel basis (sharded): %s", cudaGetErrorString(e));
 			}
 			out->kernel_dim = d;
 			out->status = GF2B200_OK;
