@@ -77,8 +77,9 @@ def rewrite_launches(src: str) -> str:
 
 def transform(text: str) -> str:
     text = rewrite_launches(text)
-    # dynamic shared memory: one process-wide buffer per name (CTAs run one at a time)
-    text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?", "extern ", text)
+    # dynamic shared memory: `extern __shared__ T name[];` -> a pointer to the running CTA's buffer
+    text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([A-Za-z_][\w ]*?)\s*\b(\w+)\[\];",
+                  r"\1 *\2 = (\1 *)emu::dynamic_smem();", text)
     return text
 
 
@@ -111,30 +112,6 @@ def build(strip_words: int = 8, force: bool = False, asan: bool = False, ubsan: 
     inc_link = out_dir / "include"
     if not inc_link.exists():
         os.symlink(ROOT / "include", inc_link)
-    # storage behind the kernels' `extern __shared__` arrays
-    (gen / "emu_shared.cpp").write_text(
-        "#include <stddef.h>\n"
-        "namespace gf2b200 {\n"
-        "alignas(128) unsigned char smem_raw[232 * 1024];\n"
-        "alignas(128) unsigned long long xs[232 * 1024 / 8];\n"
-        "}\n"
-        "#ifdef __SANITIZE_ADDRESS__\n"
-        "#include <sanitizer/asan_interface.h>\n"
-        "#endif\n"
-        "/* a launch may touch only the dynamic shared memory it asked for */\n"
-        "extern \"C\" void emu_dynamic_smem(size_t bytes) {\n"
-        "#ifdef __SANITIZE_ADDRESS__\n"
-        "\tconst size_t cap = 232 * 1024;\n"
-        "\tbytes = (bytes + 7) & ~(size_t)7;\n"
-        "\tif (bytes > cap) bytes = cap;\n"
-        "\tASAN_UNPOISON_MEMORY_REGION(gf2b200::smem_raw, cap);\n"
-        "\tASAN_UNPOISON_MEMORY_REGION(gf2b200::xs, cap);\n"
-        "\tASAN_POISON_MEMORY_REGION(gf2b200::smem_raw + bytes, cap - bytes);\n"
-        "\tASAN_POISON_MEMORY_REGION((unsigned char *)gf2b200::xs + bytes, cap - bytes);\n"
-        "#else\n"
-        "\t(void)bytes;\n"
-        "#endif\n"
-        "}\n")
     tmp = lib.with_suffix(f".tmp{os.getpid()}.so")
     san = [*(["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []),
            *(["-fsanitize=undefined", "-fno-sanitize=alignment", "-fno-sanitize-recover=undefined"] if ubsan else [])]
@@ -147,15 +124,14 @@ def build(strip_words: int = 8, force: bool = False, asan: bool = False, ubsan: 
     objs = [str(rt_obj)]
     if racecheck:
         # kernels compiled with TSan's hooks, linked against OUR implementation of them (no libtsan)
-        k_obj, s_obj, rc_obj = out_dir / "kernels.o", out_dir / "emu_shared.o", out_dir / "emu_racecheck.o"
+        k_obj, rc_obj = out_dir / "kernels.o", out_dir / "emu_racecheck.o"
         subprocess.check_call([*base, "-fsanitize=thread", "-DEMU_RACECHECK", "-c", str(gen / "gf2b200.cu.cpp"),
                                "-o", str(k_obj)])
-        subprocess.check_call([*base, "-c", str(gen / "emu_shared.cpp"), "-o", str(s_obj)])
         subprocess.check_call([*base, "-DEMU_RACECHECK", "-c", str(HERE / "emu_racecheck.cpp"), "-o", str(rc_obj)])
-        subprocess.check_call(["g++", "-shared", "-o", str(tmp), str(k_obj), str(s_obj), str(rc_obj), *objs, "-ldl"])
+        subprocess.check_call(["g++", "-shared", "-o", str(tmp), str(k_obj), str(rc_obj), *objs, "-ldl"])
     else:
         subprocess.check_call([*base, *san, *(["-fsanitize=thread"] if tsan else []), "-shared", "-o", str(tmp),
-                               str(gen / "gf2b200.cu.cpp"), str(gen / "emu_shared.cpp"), *objs, "-ldl"])
+                               str(gen / "gf2b200.cu.cpp"), *objs, "-ldl"])
     os.replace(tmp, lib)
     return lib
 

@@ -85,8 +85,8 @@ inline bool ordered(const Acc &a, bool a_shared, const emu::Fiber *f, int cta, u
 	if (a.cta != cta) return a_shared; /* shared memory of an earlier CTA is another memory */
 	if (a.tma_seq) return tma_seen >= a.tma_seq;
 	if (a.tid == (int)f->tid.x) return true;
-	if (a.bar_gen != emu::cta.bar_gen) return true;
-	if ((a.tid >> 5) == f->warp && a.warp_gen != emu::cta.w[f->warp].gen) return true;
+	if (a.bar_gen != f->cta->bar_gen) return true;
+	if ((a.tid >> 5) == f->warp && a.warp_gen != f->cta->w[f->warp].gen) return true;
 	return false;
 }
 
@@ -99,7 +99,7 @@ void report(const char *what, uintptr_t addr, bool shared, const Acc &prev, cons
 	const char *s1 = (dladdr(prev.pc, &d1) && d1.dli_sname) ? d1.dli_sname : "?";
 	fprintf(stderr,
 	        "EMU-RACECHECK hazard %s on %s memory %p (launch %u, cta %d): thread %d at +0x%lx [%s] vs thread %d%s at +0x%lx [%s]\n",
-	        what, shared ? "shared" : "device", (void *)addr, emu::launch_seq, (int)emu::g_blockIdx.x, (int)f->tid.x,
+	        what, shared ? "shared" : "device", (void *)addr, emu::launch_seq, (int)f->cta->bid.x, (int)f->tid.x,
 	        (unsigned long)((uintptr_t)pc - img_lo), s0, prev.tid, prev.tma_seq ? " (bulk copy)" : "",
 	        (unsigned long)((uintptr_t)prev.pc - img_lo), s1);
 }
@@ -109,9 +109,9 @@ void access(uintptr_t addr, size_t size, bool is_write, bool is_atomic, const vo
 	if (!f || busy || !size) return; /* host code, or the checker's own allocations */
 	if (on_fiber_stack(addr)) return;
 	if (!img_lo) dl_iterate_phdr(find_image, nullptr);
-	const bool shared = addr >= img_lo && addr < img_hi;
+	const bool shared = (addr >= img_lo && addr < img_hi) || emu::is_dynamic_smem((const void *)addr);
 	busy = true;
-	const int cta = (int)emu::g_blockIdx.x;
+	const int cta = (int)f->cta->bid.x;
 	const unsigned tma_seen = f->tma_seen;
 	for (uintptr_t a = addr; a < addr + size;) {
 		const uintptr_t cell = a >> 3;
@@ -119,7 +119,7 @@ void access(uintptr_t addr, size_t size, bool is_write, bool is_atomic, const vo
 		const unsigned n = (unsigned)((addr + size - a < 8 - off) ? addr + size - a : 8 - off);
 		const unsigned char mask = (unsigned char)(((1u << n) - 1) << off);
 		Cell &c = shadow[cell];
-		Acc me{emu::launch_seq, cta, (int)f->tid.x, emu::cta.bar_gen, emu::cta.w[f->warp].gen, tma_seq, mask,
+		Acc me{emu::launch_seq, cta, (int)f->tid.x, f->cta->bar_gen, f->cta->w[f->warp].gen, tma_seq, mask,
 		       (unsigned char)is_atomic, pc};
 		if (c.w.pc && (c.w.mask & mask) && !(c.w.atomic && is_atomic) && !ordered(c.w, shared, f, cta, tma_seen))
 			report(is_write ? "write-after-write" : "read-after-write", a, shared, c.w, f, pc);

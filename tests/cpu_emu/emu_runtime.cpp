@@ -1,9 +1,14 @@
 /*
  * emu_runtime.cpp -- TEST INFRASTRUCTURE ONLY (see include/cuda_runtime.h): the
- * fiber scheduler that runs a grid's CTAs one after another on the calling thread.
+ * fiber scheduler.  An ordinary launch runs the grid's CTAs one after another on the
+ * calling thread; a cooperative launch keeps every CTA alive and interleaves the
+ * fibers of all of them, so CTAs can wait for each other (grid barriers).
  */
 #include <cuda_runtime.h>
 #include <sys/mman.h>
+#ifdef __SANITIZE_ADDRESS__
+#include <sanitizer/asan_interface.h>
+#endif
 
 #ifdef EMU_RACECHECK
 extern "C" void emu_racecheck_launch(void);
@@ -12,9 +17,10 @@ extern "C" void emu_racecheck_launch(void);
 namespace emu {
 
 Fiber *cur = nullptr;
-Cta cta;
-dim3 g_blockIdx, g_blockDim, g_gridDim;
+Cta *cta_p = nullptr;
+dim3 g_blockDim, g_gridDim;
 void *sched_sp = nullptr;
+static std::vector<Cta *> ctas; /* CTA objects (and their dynamic shared memory), reused across launches */
 
 static const size_t STACK = 64 * 1024;
 static char *stacks = nullptr;
@@ -75,6 +81,12 @@ void warp_complete_if_ready(Warp &W) {
 	W.arrived = 0;
 }
 
+bool is_dynamic_smem(const void *p) {
+	for (const Cta *c : ctas)
+		if (c->smem && (const unsigned char *)p >= c->smem && (const unsigned char *)p < c->smem + DYN_SMEM_CAP) return true;
+	return false;
+}
+
 static void fiber_main() {
 #ifdef EMU_TSAN
 	EMU_ACQUIRE(&launch_obj);
@@ -84,14 +96,15 @@ static void fiber_main() {
 	EMU_RELEASE(&launch_obj);
 #endif
 	Fiber *f = cur;
+	Cta &C = *f->cta;
 	f->done = 1;
-	cta.alive--;
-	Warp &W = cta.w[f->warp];
+	C.alive--;
+	Warp &W = C.w[f->warp];
 	W.live &= ~(1u << f->lane);
 	warp_complete_if_ready(W);
-	if (cta.alive > 0 && cta.bar_arrived == cta.alive) { /* the rest were waiting for this one */
-		cta.bar_arrived = 0;
-		cta.bar_gen++;
+	if (C.alive > 0 && C.bar_arrived == C.alive) { /* the rest were waiting for this one */
+		C.bar_arrived = 0;
+		C.bar_gen++;
 	}
 	TSAN_TO(sched_tsan);
 	emu_switch(&f->sp, sched_sp);
@@ -99,25 +112,103 @@ static void fiber_main() {
 }
 
 static bool runnable(const Fiber &f) {
+	const Cta &C = *f.cta;
 	switch (f.wait) {
 	case W_NONE: return true;
-	case W_BARRIER: return f.bar_gen != cta.bar_gen;
-	case W_WARP_ENTER: return cta.w[f.warp].departing == 0;
-	case W_WARP_RESULT: return (cta.w[f.warp].departing >> f.lane) & 1;
+	case W_BARRIER: return f.bar_gen != C.bar_gen;
+	case W_WARP_ENTER: return C.w[f.warp].departing == 0;
+	case W_WARP_RESULT: return (C.w[f.warp].departing >> f.lane) & 1;
 	case W_WORD: return (__atomic_load_n((const unsigned long long *)f.word, __ATOMIC_ACQUIRE) & 1) != f.word_val;
 	}
 	return true;
 }
 
-void run_grid(dim3 grid, dim3 block, void (*thunk)(void *), void *arg) {
+/* (re)initialise CTA object `ci` as block `bx` of the grid; its fibers use stacks [stack0, stack0 + nt) */
+static void cta_start(size_t ci, unsigned bx, dim3 block, size_t nt, size_t stack0, size_t smem) {
+	while (ctas.size() <= ci) ctas.push_back(new Cta());
+	Cta &C = *ctas[ci];
+	if (!C.smem && posix_memalign((void **)&C.smem, 1024, DYN_SMEM_CAP)) abort();
+#ifdef __SANITIZE_ADDRESS__
+	/* a launch may touch only the dynamic shared memory it asked for */
+	ASAN_UNPOISON_MEMORY_REGION(C.smem, DYN_SMEM_CAP);
+	const size_t keep = (smem + 7) & ~(size_t)7;
+	if (keep < DYN_SMEM_CAP) ASAN_POISON_MEMORY_REGION(C.smem + keep, DYN_SMEM_CAP - keep);
+#else
+	(void)smem;
+#endif
+	C.f.resize(nt);
+	C.w.resize((nt + 31) / 32);
+	C.bid = dim3(bx);
+	C.alive = (int)nt;
+	C.bar_arrived = 0;
+	C.bar_gen = 0;
+	C.tma_count = 0;
+	for (Warp &W : C.w) memset(&W, 0, sizeof W);
+	for (size_t t = 0; t < nt; t++) {
+		Fiber &f = C.f[t];
+		f.done = 0;
+		f.wait = W_NONE;
+		f.tma_seen = 0;
+		f.cta = &C;
+		f.tid = dim3((unsigned)(t % block.x), (unsigned)(t / block.x));
+		f.lane = (int)(t & 31);
+		f.warp = (int)(t >> 5);
+		C.w[f.warp].live |= 1u << f.lane;
+		/* initial frame: six callee-saved slots, then the entry point as return address;
+		 * after the `ret` rsp is 8 mod 16 as at any function entry */
+		uintptr_t top = ((uintptr_t)(stacks + (stack0 + t + 1) * STACK)) & ~(uintptr_t)15;
+		void **sp = (void **)(top - 8);
+		*--sp = (void *)fiber_main;
+		for (int i = 0; i < 6; i++) *--sp = nullptr;
+		f.sp = sp;
+#ifdef EMU_TSAN
+		if (stack0 + t >= tsan_fibers.size()) tsan_fibers.resize(stack0 + t + 1, nullptr);
+		if (!tsan_fibers[stack0 + t]) tsan_fibers[stack0 + t] = __tsan_create_fiber(0);
+		f.tsan = tsan_fibers[stack0 + t];
+#endif
+	}
+}
+
+/* run the fibers of CTA objects [0, n) until all are done */
+static void run_ctas(size_t n, size_t nt) {
+	size_t remaining = n * nt;
+	while (remaining > 0) {
+		bool progress = false;
+		for (size_t ci = 0; ci < n; ci++) {
+			Cta &C = *ctas[ci];
+			if (!C.alive) continue;
+			for (size_t t = 0; t < nt; t++) {
+				Fiber &f = C.f[t];
+				if (f.done || !runnable(f)) continue;
+				/* a thread that merely yielded (spin wait) counts as progress only if
+				 * something else moves too; a grid where everybody spins is a deadlock
+				 * that the caller's own time-out has to break */
+				f.wait = W_NONE;
+				cur = &f;
+				cta_p = &C;
+				TSAN_TO(f.tsan);
+				emu_switch(&sched_sp, f.sp);
+				progress = true;
+				if (f.done) remaining--;
+			}
+		}
+		if (!progress) {
+			fprintf(stderr, "emu: deadlock (%zu threads parked)\n", remaining);
+			abort();
+		}
+	}
+}
+
+void run_grid(dim3 grid, dim3 block, size_t smem, bool concurrent, void (*thunk)(void *), void *arg) {
 	const size_t nt = (size_t)block.x * block.y * block.z;
-	if (nt > n_stacks) {
+	const size_t need = concurrent ? nt * grid.x : nt;
+	if (need > n_stacks) {
 		if (stacks) munmap(stacks, n_stacks * STACK);
-		stacks = (char *)mmap(nullptr, nt * STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+		stacks = (char *)mmap(nullptr, need * STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
 		if (stacks == MAP_FAILED) abort();
-		n_stacks = nt;
+		n_stacks = need;
 		stacks_base = stacks;
-		stacks_bytes = nt * STACK;
+		stacks_bytes = need * STACK;
 	}
 	launch_seq++;
 #ifdef EMU_RACECHECK
@@ -127,63 +218,24 @@ void run_grid(dim3 grid, dim3 block, void (*thunk)(void *), void *arg) {
 	g_arg = arg;
 	g_gridDim = grid;
 	g_blockDim = block;
-	cta.f.resize(nt);
-	cta.w.resize((nt + 31) / 32);
 #ifdef EMU_TSAN
 	sched_tsan = __tsan_get_current_fiber();
 	EMU_RELEASE(&launch_obj);
 #endif
-	for (unsigned bx = 0; bx < grid.x; bx++) {
-		g_blockIdx = dim3(bx);
-		cta.alive = (int)nt;
-		cta.bar_arrived = 0;
-		cta.bar_gen = 0;
-		cta.tma_count = 0;
-		for (Warp &W : cta.w) memset(&W, 0, sizeof W);
-		for (size_t t = 0; t < nt; t++) {
-			Fiber &f = cta.f[t];
-			f.done = 0;
-			f.wait = W_NONE;
-			f.tma_seen = 0;
-			f.tid = dim3((unsigned)(t % block.x), (unsigned)(t / block.x));
-			f.lane = (int)(t & 31);
-			f.warp = (int)(t >> 5);
-			cta.w[f.warp].live |= 1u << f.lane;
-			/* initial frame: six callee-saved slots, then the entry point as return address;
-			 * after the `ret` rsp is 8 mod 16 as at any function entry */
-			uintptr_t top = ((uintptr_t)(stacks + (t + 1) * STACK)) & ~(uintptr_t)15;
-			void **sp = (void **)(top - 8);
-			*--sp = (void *)fiber_main;
-			for (int i = 0; i < 6; i++) *--sp = nullptr;
-			f.sp = sp;
-#ifdef EMU_TSAN
-			if (t >= tsan_fibers.size()) tsan_fibers.push_back(__tsan_create_fiber(0));
-			f.tsan = tsan_fibers[t];
-#endif
-		}
-		int remaining = (int)nt;
-		while (remaining > 0) {
-			bool progress = false;
-			for (size_t t = 0; t < nt; t++) {
-				Fiber &f = cta.f[t];
-				if (f.done || !runnable(f)) continue;
-				f.wait = W_NONE;
-				cur = &f;
-				TSAN_TO(f.tsan);
-				emu_switch(&sched_sp, f.sp);
-				progress = true;
-				if (f.done) remaining--;
-			}
-			if (!progress) {
-				fprintf(stderr, "emu: deadlock in CTA %u (%d threads parked)\n", bx, remaining);
-				abort();
-			}
+	if (concurrent) {
+		for (unsigned bx = 0; bx < grid.x; bx++) cta_start(bx, bx, block, nt, (size_t)bx * nt, smem);
+		run_ctas(grid.x, nt);
+	} else {
+		for (unsigned bx = 0; bx < grid.x; bx++) {
+			cta_start(0, bx, block, nt, 0, smem);
+			run_ctas(1, nt);
 		}
 	}
 #ifdef EMU_TSAN
 	EMU_ACQUIRE(&launch_obj);
 #endif
 	cur = nullptr;
+	cta_p = nullptr;
 }
 
 } /* namespace emu */

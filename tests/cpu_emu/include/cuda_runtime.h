@@ -85,6 +85,7 @@ struct Warp {
 	unsigned snap_mask; /* lanes that contributed to snap */
 };
 
+struct Cta;
 struct Fiber {
 	void *sp;
 	int done;
@@ -94,6 +95,7 @@ struct Fiber {
 	unsigned long long word_val;
 	dim3 tid;
 	int lane, warp;
+	Cta *cta;
 	void *tsan; /* TSan fiber handle (ThreadSanitizer builds) */
 	unsigned tma_seen; /* racecheck: bulk copies of this CTA whose mbarrier phase this thread has waited for */
 };
@@ -104,16 +106,20 @@ struct Cta {
 	int alive, bar_arrived;
 	unsigned bar_gen;
 	unsigned tma_count; /* bulk copies issued in this CTA so far */
+	dim3 bid;
+	unsigned char *smem; /* this CTA's dynamic shared memory */
 };
 
 extern Fiber *cur;
-extern Cta cta;
-extern dim3 g_blockIdx, g_blockDim, g_gridDim;
+extern Cta *cta_p; /* the CTA of the running fiber */
+extern dim3 g_blockDim, g_gridDim;
 extern void *sched_sp;
+static const size_t DYN_SMEM_CAP = 232 * 1024;
 
 extern "C" void emu_switch(void **save_sp, void *new_sp);
 void yield_to_scheduler();
-void run_grid(dim3 grid, dim3 block, void (*thunk)(void *), void *arg);
+void run_grid(dim3 grid, dim3 block, size_t smem, bool concurrent, void (*thunk)(void *), void *arg);
+bool is_dynamic_smem(const void *p);
 void warp_complete_if_ready(Warp &W);
 
 EMU_INTERNAL static inline void block_on(int kind) {
@@ -123,7 +129,7 @@ EMU_INTERNAL static inline void block_on(int kind) {
 
 /* every live lane deposits v; returns the snapshot of all lanes (0 for dead lanes) */
 EMU_INTERNAL static inline const unsigned long long *warp_exchange(unsigned long long v, unsigned *mask_out = nullptr) {
-	Warp &W = cta.w[cur->warp];
+	Warp &W = cta_p->w[cur->warp];
 	const unsigned bit = 1u << cur->lane;
 	while (W.departing) block_on(W_WARP_ENTER);
 	W.vals[cur->lane] = v;
@@ -140,7 +146,9 @@ EMU_INTERNAL static inline const unsigned long long *warp_exchange(unsigned long
 }
 
 EMU_INTERNAL static inline const dim3 &self_tid() { return cur->tid; }
-EMU_INTERNAL static inline const dim3 &self_bid() { return g_blockIdx; }
+EMU_INTERNAL static inline const dim3 &self_bid() { return cta_p->bid; }
+/* `extern __shared__ T name[]` is rewritten by build_emu.py into a pointer to this */
+EMU_INTERNAL static inline void *dynamic_smem() { return cta_p->smem; }
 EMU_INTERNAL static inline const dim3 &self_bdim() { return g_blockDim; }
 EMU_INTERNAL static inline const dim3 &self_gdim() { return g_gridDim; }
 
@@ -153,7 +161,7 @@ EMU_INTERNAL static inline const dim3 &self_gdim() { return g_gridDim; }
 
 /* ---- device intrinsics ---------------------------------------------------- */
 EMU_INTERNAL static inline void __syncthreads() {
-	emu::Cta &C = emu::cta;
+	emu::Cta &C = *emu::cta_p;
 	EMU_RELEASE(&C.bar_gen);
 	C.bar_arrived++;
 	if (C.bar_arrived == C.alive) {
@@ -221,7 +229,8 @@ template <typename T> static inline void __stcg(T *p, const T &v) { *p = v; }
 static inline void __threadfence() {}
 static inline void __threadfence_system() {}
 static inline void __threadfence_block() {}
-static inline void __nanosleep(unsigned) {}
+/* a spinning thread lets the others run (CTAs of a cooperative launch wait for each other) */
+EMU_INTERNAL static inline void __nanosleep(unsigned) { emu::block_on(emu::W_NONE); }
 static inline int atomicOr(int *p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
@@ -250,9 +259,9 @@ extern "C" void emu_racecheck_bulk_write(void *dst, size_t bytes, unsigned seq);
 /* the bulk copy (TMA stand-in): done at once, completes the barrier's current phase */
 EMU_INTERNAL static inline void emu_bulk_copy(void *dst, const void *src, unsigned bytes, void *bar) {
 	memcpy(dst, src, bytes);
-	emu::cta.tma_count++;
+	emu::cta_p->tma_count++;
 #ifdef EMU_RACECHECK
-	emu_racecheck_bulk_write(dst, bytes, emu::cta.tma_count);
+	emu_racecheck_bulk_write(dst, bytes, emu::cta_p->tma_count);
 #endif
 	emu_mbar_complete(bar);
 }
@@ -264,7 +273,7 @@ EMU_INTERNAL static inline void emu_mbar_wait(void *bar, unsigned phase) {
 		emu::block_on(emu::W_WORD);
 	}
 	EMU_ACQUIRE(bar);
-	emu::cur->tma_seen = emu::cta.tma_count;
+	emu::cur->tma_seen = emu::cta_p->tma_count;
 }
 
 /* ---- runtime API ------------------------------------------------------------ */
@@ -336,12 +345,33 @@ template <typename... P> struct Call {
 		std::apply(c->k, c->args);
 	}
 };
-extern "C" void emu_dynamic_smem(size_t bytes); /* ASan builds: poison what the launch did not ask for */
 template <typename... P, typename... A>
-static inline void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, void (*k)(P...), A &&...a) {
+static inline void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, bool concurrent, void (*k)(P...), A &&...a) {
 	Call<P...> c{k, std::tuple<std::decay_t<P>...>(std::forward<A>(a)...)};
-	emu_dynamic_smem(smem);
-	run_grid(grid, block, &Call<P...>::thunk, &c);
+	run_grid(grid, block, smem, concurrent, &Call<P...>::thunk, &c);
 }
 } /* namespace emu */
-#define EMU_LAUNCH(k, g, b, smem, st, ...) emu::launch(dim3(g), dim3(b), (size_t)(smem), (st), k, ##__VA_ARGS__)
+
+/* cooperative launches: every CTA of the grid is resident at once -- the emulator then
+ * interleaves the fibers of ALL CTAs (kernels launched this way must keep their shared
+ * memory dynamic: static __shared__ variables are one process-wide instance here) */
+enum cudaLaunchAttributeID { cudaLaunchAttributeCooperative = 2 };
+struct cudaLaunchAttributeValue { int cooperative; };
+struct cudaLaunchAttribute { cudaLaunchAttributeID id; cudaLaunchAttributeValue val; };
+struct cudaLaunchConfig_t { /* same member ORDER as CUDA's (callers use positional initialisation:
+	                            * gridDim / blockDim are macros in this header) */
+	dim3 grid_, block_;
+	size_t dynamicSmemBytes;
+	cudaStream_t stream;
+	cudaLaunchAttribute *attrs;
+	unsigned numAttrs;
+};
+template <typename... P, typename... A>
+static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t *cfg, void (*k)(P...), A &&...a) {
+	bool coop = false;
+	for (unsigned i = 0; i < cfg->numAttrs; i++)
+		if (cfg->attrs[i].id == cudaLaunchAttributeCooperative && cfg->attrs[i].val.cooperative) coop = true;
+	emu::launch(cfg->grid_, cfg->block_, cfg->dynamicSmemBytes, cfg->stream, coop, k, std::forward<A>(a)...);
+	return cudaSuccess;
+}
+#define EMU_LAUNCH(k, g, b, smem, st, ...) emu::launch(dim3(g), dim3(b), (size_t)(smem), (st), false, k, ##__VA_ARGS__)

@@ -70,3 +70,31 @@ def test_emulated_library_is_not_the_product():
         assert _shim.LIB_PATH == ROOT / "gf2bv_b200" / "libgf2b200.so"
     src = (ROOT / "__graft_entry__.py").read_text() + (ROOT / "gf2bv_b200" / "_shim.py").read_text()
     assert "cpu_emu" not in src
+
+
+def _selftest(tmp_path, src, defines=(), kernel_flags=(), extra=()):
+    emu = ROOT / "tests" / "cpu_emu"
+    base = ["g++", "-O1", "-g", "-std=c++17", "-w", "-I", str(emu / "include"), *defines]
+    objs = []
+    for name, flags in [("emu_runtime.cpp", ())] + [(e, ()) for e in extra]:
+        o = tmp_path / (name + ".o")
+        subprocess.check_call([*base, *flags, "-c", str(emu / name), "-o", str(o)])
+        objs.append(str(o))
+    k = tmp_path / "kernel.o"
+    subprocess.check_call([*base, *kernel_flags, "-c", str(emu / "selftest" / src), "-o", str(k)])
+    exe = tmp_path / "selftest"
+    subprocess.check_call(["g++", str(k), *objs, "-ldl", "-o", str(exe)])
+    return subprocess.run([str(exe)], capture_output=True, text=True)
+
+
+def test_emulator_cooperative_launch_with_grid_barrier(tmp_path):
+    """CTAs of a cooperative launch are interleaved, so they can wait for each other"""
+    r = _selftest(tmp_path, "coop_test.cpp")
+    assert r.returncode == 0 and "coop test: ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_hazard_checker_positive_control(tmp_path):
+    """a kernel with a missing __syncthreads is reported, the same kernel with it is not (1024 threads)"""
+    r = _selftest(tmp_path, "racecheck_test.cpp", defines=("-DEMU_RACECHECK",), kernel_flags=("-fsanitize=thread",),
+                  extra=("emu_racecheck.cpp",))
+    assert r.returncode == 0 and "ok kernel: 0 hazards" in r.stdout, r.stdout + r.stderr[-2000:]
