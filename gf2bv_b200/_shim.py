@@ -80,6 +80,10 @@ def lib() -> ctypes.CDLL:
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
             " -- gf2bv_b200 has no CPU fallback")
     L = ctypes.CDLL(str(LIB_PATH), mode=ctypes.RTLD_GLOBAL)
+    if hasattr(L, "gf2b200_emulated_build") and os.environ.get("GF2B200_TEST_EMULATION") != "1":
+        # the kernel tests' CPU emulation build is test infrastructure, never a way to run without a GPU
+        raise Gf2b200Error(f"{LIB_PATH} is the CPU emulation build of the kernel tests; refusing to use it -- "
+                           "gf2bv_b200 has no CPU fallback")
     vp, u64p, i64 = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64
     L.gf2b200_abi_version.restype = ctypes.c_int
     L.gf2b200_device_count.restype = ctypes.c_int

@@ -86,6 +86,18 @@ static int shim_load(void) {
 		             path, dlerror());
 		return -1;
 	}
+	/* tests/cpu_emu builds a CPU emulation of the kernels for kernel tests; such a build is
+	 * never a way to run this extension without a GPU unless a test says so explicitly */
+	if (dlsym(h, "gf2b200_emulated_build")) {
+		const char *ok = getenv("GF2B200_TEST_EMULATION");
+		if (!ok || strcmp(ok, "1") != 0) {
+			PyErr_Format(PyExc_RuntimeError,
+			             "gf2b200: %s is the CPU emulation build of tests/cpu_emu (test infrastructure); "
+			             "refusing to use it -- there is no CPU fallback", path);
+			dlclose(h);
+			return -1;
+		}
+	}
 	shim_t s;
 	memset(&s, 0, sizeof s);
 	s.handle = h;

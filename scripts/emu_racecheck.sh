@@ -10,7 +10,7 @@ set -u
 SWORDS=${1:-8}; shift || true
 LIB=$(python tests/cpu_emu/build_emu.py --strip-words $SWORDS --racecheck | tail -1)
 LOG=$(mktemp)
-GF2B200_LIB=$LIB python -m pytest tests/test_gpu_solver.py tests/test_gpu_sharded.py tests/test_gpu_api.py -m gpu -x -q -p no:cacheprovider \
+GF2B200_TEST_EMULATION=1 GF2B200_LIB=$LIB python -m pytest tests/test_gpu_solver.py tests/test_gpu_sharded.py tests/test_gpu_api.py -m gpu -x -q -p no:cacheprovider \
   -k "not 32768 and not mt19937 and not 8192 and not 1025-3000 and not 2000-1500 and not 4099 and not 5000 and not 4096 and not 0.001 and not 2100 and not bignull" "$@" 2>&1 | tee $LOG | grep -v "^EMU-RACECHECK hazard" | tail -5
 grep "^EMU-RACECHECK hazard" $LOG | head -20
 N=$(grep -c "^EMU-RACECHECK hazard" $LOG); rm -f $LOG

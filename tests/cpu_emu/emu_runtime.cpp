@@ -14,6 +14,9 @@
 extern "C" void emu_racecheck_launch(void);
 #endif
 
+/* marker: the package refuses a library that exports this unless GF2B200_TEST_EMULATION=1 */
+extern "C" int gf2b200_emulated_build(void) { return 1; }
+
 namespace emu {
 
 Fiber *cur = nullptr;

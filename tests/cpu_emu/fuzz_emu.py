@@ -2,7 +2,7 @@
 (tests/cpu_emu) against the oracle -- single-shard and loopback-sharded contexts,
 modes 0 and 1.  Run it with the emulated library selected:
 
-    GF2B200_LIB=$(python tests/cpu_emu/build_emu.py) python tests/cpu_emu/fuzz_emu.py [seconds] [seed]
+    GF2B200_TEST_EMULATION=1 GF2B200_LIB=$(python tests/cpu_emu/build_emu.py) python tests/cpu_emu/fuzz_emu.py [seconds] [seed]
 """
 import random
 import sys

@@ -36,7 +36,7 @@ def emu_runs():
     procs = {}
     for sw in (16, 8):
         lib = build_emu.build(sw)
-        env = dict(os.environ, GF2B200_LIB=str(lib), GF2_EMU_SMS="3")
+        env = dict(os.environ, GF2B200_LIB=str(lib), GF2_EMU_SMS="3", GF2B200_TEST_EMULATION="1")
         procs[sw] = subprocess.Popen(
             [sys.executable, "-m", "pytest", "tests/test_gpu_solver.py", "tests/test_gpu_sharded.py",
              "tests/test_gpu_api.py", "-m", "gpu",
@@ -63,13 +63,21 @@ def test_gpu_parity_suite_on_emulated_kernels(emu_runs, strip_words):
 
 
 def test_emulated_library_is_not_the_product():
-    """the package never points at the emulated build by itself"""
+    """the package never points at the emulated build by itself, and refuses it when pointed
+    at it without the tests' explicit switch (ctypes shim and CPython extension alike)"""
+    import build_emu
     from gf2bv_b200 import _shim
 
     if not os.environ.get("GF2B200_LIB"):
         assert _shim.LIB_PATH == ROOT / "gf2bv_b200" / "libgf2b200.so"
     src = (ROOT / "__graft_entry__.py").read_text() + (ROOT / "gf2bv_b200" / "_shim.py").read_text()
     assert "cpu_emu" not in src
+    env = {k: v for k, v in os.environ.items() if k != "GF2B200_TEST_EMULATION"}
+    env["GF2B200_LIB"] = str(build_emu.build(8))
+    for code in ("from gf2bv_b200 import _shim; _shim.Context(0)",
+                 "from gf2bv_b200 import _internal; _internal.m4ri_solve([3, 2], 1, 0)"):
+        r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True)
+        assert r.returncode != 0 and "emulation build" in r.stderr, r.stderr[-500:]
 
 
 def _selftest(tmp_path, src, defines=(), kernel_flags=(), extra=()):
