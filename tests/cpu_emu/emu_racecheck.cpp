@@ -18,15 +18,18 @@
  *   - for data written by the bulk copy (TMA stand-in): the reader has waited on the
  *     mbarrier phase that the copy completed,
  *   - both are atomics.
- * Different CTAs of one launch are never ordered (the "last CTA" ticket pattern of
- * SWEEP_TAIL_SELECT is therefore reported; it is ordered by fence + atomic, which
- * this model does not follow).
+ * Different CTAs of one launch are ordered only through the ticket pattern
+ * "__threadfence; __syncthreads; one thread does an atomic RMW on X" in CTA c1 and a LATER
+ * atomic RMW on the same X in CTA c2: what c1 did before that barrier is then ordered before
+ * what c2 does after the atomic (same thread) or after c2's next barrier (other threads).
+ * (The last-CTA scan of SWEEP_TAIL_SELECT and grid barriers are built from exactly this.)
  */
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <link.h>
 
 #include <unordered_map>
+#include <vector>
 
 namespace emu {
 extern char *stacks_base;
@@ -51,6 +54,14 @@ struct Cell {
 };
 
 std::unordered_map<uintptr_t, Cell> shadow;
+
+/* inter-CTA ordering through atomics: per atomic address, what each CTA has released there;
+ * per CTA, what it has acquired from every other CTA */
+struct Rel { int cta; unsigned bar_gen; };                  /* accesses of `cta` with generation < bar_gen */
+struct Acq { unsigned upto; unsigned since_gen; int by_tid; }; /* ... are visible to accesses after since_gen (or to by_tid at once) */
+std::unordered_map<uintptr_t, std::vector<Rel>> released;   /* keyed by the atomic's address */
+std::unordered_map<long long, Acq> acquired;                /* key = (acquiring cta << 32) | releasing cta */
+inline long long akey(int to, int from) { return ((long long)to << 32) | (unsigned)from; }
 uintptr_t img_lo = 0, img_hi = 0;
 unsigned long n_hazards = 0, n_reported = 0;
 bool busy = false;
@@ -82,7 +93,13 @@ inline bool on_fiber_stack(uintptr_t a) {
 /* is the earlier access `a` ordered before the current access of thread f? */
 inline bool ordered(const Acc &a, bool a_shared, const emu::Fiber *f, int cta, unsigned tma_seen) {
 	if (a.launch != emu::launch_seq) return true;
-	if (a.cta != cta) return a_shared; /* shared memory of an earlier CTA is another memory */
+	if (a.cta != cta) {
+		if (a_shared) return true; /* shared memory of an earlier CTA is another memory */
+		auto it = acquired.find(akey(cta, a.cta));
+		/* an atomic on the ticket word itself is ordered by the atomics' own order */
+		if (it == acquired.end() || (a.atomic ? a.bar_gen > it->second.upto : a.bar_gen >= it->second.upto)) return false;
+		return f->cta->bar_gen > it->second.since_gen || (int)f->tid.x == it->second.by_tid;
+	}
 	if (a.tma_seq) return tma_seen >= a.tma_seq;
 	if (a.tid == (int)f->tid.x) return true;
 	if (a.bar_gen != f->cta->bar_gen) return true;
@@ -141,6 +158,29 @@ void access(uintptr_t addr, size_t size, bool is_write, bool is_atomic, const vo
 	busy = false;
 }
 
+/* an atomic read-modify-write on device memory: release what this CTA did before its last
+ * barrier, acquire what other CTAs released here earlier */
+void atomic_rmw(uintptr_t addr) {
+	const emu::Fiber *f = emu::cur;
+	if (!f || busy) return;
+	busy = true;
+	const int me = (int)f->cta->bid.x;
+	std::vector<Rel> &rl = released[addr];
+	for (const Rel &r : rl)
+		if (r.cta != me) {
+			Acq &q = acquired[akey(me, r.cta)];
+			if (r.bar_gen > q.upto || q.upto == 0) q = Acq{r.bar_gen, f->cta->bar_gen, (int)f->tid.x};
+		}
+	bool found = false;
+	for (Rel &r : rl)
+		if (r.cta == me) {
+			r.bar_gen = f->cta->bar_gen;
+			found = true;
+		}
+	if (!found) rl.push_back(Rel{me, f->cta->bar_gen});
+	busy = false;
+}
+
 #define PC __builtin_return_address(0)
 
 } /* namespace */
@@ -162,6 +202,8 @@ extern "C" void emu_racecheck_launch(void) {
 	}
 	busy = true;
 	shadow.clear();
+	released.clear();
+	acquired.clear();
 	busy = false;
 }
 
@@ -204,10 +246,12 @@ void __tsan_atomic32_store(volatile int *p, int v, int) {
 }
 int __tsan_atomic32_fetch_or(volatile int *p, int v, int) {
 	access((uintptr_t)p, 4, true, true, PC);
+	atomic_rmw((uintptr_t)p);
 	return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST);
 }
 int __tsan_atomic32_fetch_add(volatile int *p, int v, int) {
 	access((uintptr_t)p, 4, true, true, PC);
+	atomic_rmw((uintptr_t)p);
 	return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
 }
 long long __tsan_atomic64_load(const volatile long long *p, int) {
@@ -220,14 +264,17 @@ void __tsan_atomic64_store(volatile long long *p, long long v, int) {
 }
 long long __tsan_atomic64_fetch_add(volatile long long *p, long long v, int) {
 	access((uintptr_t)p, 8, true, true, PC);
+	atomic_rmw((uintptr_t)p);
 	return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
 }
 long long __tsan_atomic64_fetch_or(volatile long long *p, long long v, int) {
 	access((uintptr_t)p, 8, true, true, PC);
+	atomic_rmw((uintptr_t)p);
 	return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST);
 }
 long long __tsan_atomic64_fetch_xor(volatile long long *p, long long v, int) {
 	access((uintptr_t)p, 8, true, true, PC);
+	atomic_rmw((uintptr_t)p);
 	return __atomic_fetch_xor(p, v, __ATOMIC_SEQ_CST);
 }
 }

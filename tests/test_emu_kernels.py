@@ -106,3 +106,4 @@ def test_hazard_checker_positive_control(tmp_path):
     r = _selftest(tmp_path, "racecheck_test.cpp", defines=("-DEMU_RACECHECK",), kernel_flags=("-fsanitize=thread",),
                   extra=("emu_racecheck.cpp",))
     assert r.returncode == 0 and "ok kernel: 0 hazards" in r.stdout, r.stdout + r.stderr[-2000:]
+    assert "ticket kernel: 0 hazards" in r.stdout and "no-ticket kernel: 0 hazards" not in r.stdout, r.stdout
