@@ -524,6 +524,11 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
  * r01e_ab.txt): neither 622.6 ms per solve, early tile alone 608.8 ms, both 626 ms --
  * the early tile hides the TMA round trip of ~14 strip changes per CTA and launch, the
  * early loads lengthen the build (registers held across it) by more than they hide. */
+#ifndef SWEEP_UNCOND_LOADS
+/* profiles/r01g_sweep_hotspots.md: ~11 % of the stall samples sit on the coefficient load that
+ * gates the row loads; 1 = issue the row loads unconditionally.  Not yet timed on a GPU. */
+#define SWEEP_UNCOND_LOADS 0
+#endif
 #ifndef SWEEP_EARLY_LOADS
 #define SWEEP_EARLY_LOADS 0 /* issue a unit's row loads before the table build of its strip */
 #endif
@@ -838,7 +843,14 @@ sweep_body(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_c
 		for (int q = 0; q < SWEEP_U; q++) {
 			long long row = row0 + (SWEEP_THREADS / SQ) * q;
 			act[q] = (row < m) && (cf[q] != 0 || force);
+#if SWEEP_UNCOND_LOADS
+			/* do not wait for the coefficient before asking for the row piece: the two
+			 * loads overlap instead of chaining (rows with a zero coefficient -- rare on
+			 * dense systems -- are then read for nothing, never written) */
+			if (row < m) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ);
+#else
 			if (act[q]) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ);
+#endif
 		}
 #if SWEEP_EARLY_LOADS
 		enter_strip(s, u); /* this unit's row pieces are already in flight during the build */
