@@ -976,7 +976,7 @@ __global__ void k_check(Mat M, SolverState *st) {
 __global__ void __launch_bounds__(1024, 1)
 k_backsub(Mat M, const long long *__restrict__ hist_r, const u64 *__restrict__ hist_pm,
           const long long *__restrict__ freecols, int use_b, u64 *__restrict__ xout) {
-	extern __shared__ u64 xs[];
+	extern __shared__ __align__(128) u64 xs[];
 	__shared__ unsigned long long newbits;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int WT = M.ns * SW;
