@@ -524,6 +524,12 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
  * r01e_ab.txt): neither 622.6 ms per solve, early tile alone 608.8 ms, both 626 ms --
  * the early tile hides the TMA round trip of ~14 strip changes per CTA and launch, the
  * early loads lengthen the build (registers held across it) by more than they hide. */
+#ifndef SWEEP_PC_SHFL
+/* 1: the coefficient of a row is loaded by one of the SQ threads that share the row and
+ * passed on by warp shuffle (the global side of the l1tex pipe costs 12.8 wavefronts per warp
+ * where 8 are needed; the SQ-fold coefficient load is 2 of them).  Not yet timed on a GPU. */
+#define SWEEP_PC_SHFL 0
+#endif
 #ifndef SWEEP_UNCOND_LOADS
 /* profiles/r01g_sweep_hotspots.md: ~11 % of the stall samples sit on the coefficient load that
  * gates the row loads; 1 = issue the row loads unconditionally.  Not yet timed on a GPU. */
@@ -837,7 +843,13 @@ sweep_body(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_c
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {
 			long long row = row0 + (SWEEP_THREADS / SQ) * q;
+#if SWEEP_PC_SHFL
+			/* one lane per row loads the coefficient, its SQ - 1 neighbours get it by shuffle */
+			u64 c = (ch == 0 && row < m) ? (__ldg(pc_cur + row) & pm) : 0;
+			cf[q] = shfl64(c, (tid & 31) & ~(SQ - 1));
+#else
 			cf[q] = (row < m) ? (__ldg(pc_cur + row) & pm) : 0;
+#endif
 		}
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {

@@ -6,7 +6,7 @@
 set -eu
 mkdir -p gf2bv_b200/variants
 if [ $# -eq 0 ]; then
-  set -- "tailsel:-DSWEEP_TAIL_SELECT=1" "uncond:-DSWEEP_UNCOND_LOADS=1" "pad4:-DSWEEP_SEL_PAD=4" "pad8:-DSWEEP_SEL_PAD=8" \
+  set -- "tailsel:-DSWEEP_TAIL_SELECT=1" "uncond:-DSWEEP_UNCOND_LOADS=1" "pcshfl:-DSWEEP_PC_SHFL=1" "pad4:-DSWEEP_SEL_PAD=4" "pad8:-DSWEEP_SEL_PAD=8" \
          "notile:-DSWEEP_EARLY_TILE=0" "u3:-DSWEEP_U=3" "s128:-DGF2_STRIP_WORDS=16"
 fi
 for v in "$@"; do
