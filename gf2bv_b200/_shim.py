@@ -61,6 +61,7 @@ class CStats(ctypes.Structure):
         ("sweep_bytes_max", ctypes.c_double),
         ("sweep_bytes_timed", ctypes.c_double),
         ("sweep_launches_timed", ctypes.c_int64),
+        ("forward_kernel_launches", ctypes.c_int64),
     ]
 
     def as_dict(self):

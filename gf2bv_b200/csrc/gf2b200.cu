@@ -17,6 +17,7 @@
  *             kind, so the sharded path can be parity-tested on one GPU.
  */
 #include "gf2b200_dist.cuh"
+#include "gf2b200_persist.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -52,6 +53,7 @@ struct gf2b200_ctx {
 	int profile;
 	int rank, world; /* shard index of the first local shard, number of shards */
 	int n_local;     /* local shards: 1 (single, nccl) or world (loopback) */
+	int persist;     /* the one-kernel forward elimination (k_forward) can be launched cooperatively */
 	ncclComm_t nccl; /* nccl contexts */
 	struct gf2b200_system *cached; /* device buffers of the last gf2b200_solve, reused for equal shapes */
 	char err[512];
@@ -67,6 +69,10 @@ struct Shard {
 	long long *d_hist_r;
 	u64 *d_hist_pm;
 	uint4 *d_ebuf;
+	/* one-GPU systems: second E-tile buffer, barrier block and per-panel timestamps of k_forward */
+	uint4 *d_ebuf2;
+	void *d_gs;
+	unsigned long long *d_tpanel;
 	/* sharded systems only */
 	DistPanel *d_dp;
 	unsigned char *d_hist_owner;
@@ -191,6 +197,23 @@ static int ctx_init(gf2b200_ctx **out, int device) {
 			if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 		}
 	}
+#if SW == 8
+	/* the one-kernel forward elimination needs every CTA of a grid of n_sm resident at once
+	 * (cooperative launch); GF2B200_FORWARD=launches keeps the per-panel launch chain */
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, PERSIST_SMEM);
+	if (e == cudaSuccess) {
+		const char *fw = getenv("GF2B200_FORWARD");
+		c->persist = !(fw && !strcmp(fw, "launches"));
+#ifndef GF2_EMU
+		int coop = 0, per_sm = 0;
+		if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess) coop = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_forward, SWEEP_THREADS, PERSIST_SMEM) != cudaSuccess)
+			per_sm = 0;
+		cudaGetLastError();
+		if (!coop || per_sm < 1) c->persist = 0;
+#endif
+	}
+#endif
 	if (e != cudaSuccess) {
 		int rc = fail(nullptr, GF2B200_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
 		free(c);
@@ -305,6 +328,9 @@ static void shard_free(Shard &s) {
 	cudaFree(s.d_hist_r);
 	cudaFree(s.d_hist_pm);
 	cudaFree(s.d_ebuf);
+	cudaFree(s.d_ebuf2);
+	cudaFree(s.d_gs);
+	cudaFree(s.d_tpanel);
 	for (void *p : s.ipc_opened) cudaIpcCloseMemHandle(p);
 	s.ipc_opened.clear();
 	cudaFree(s.d_dp);
@@ -323,7 +349,7 @@ extern "C" void gf2b200_system_destroy(gf2b200_system *sys) {
 	delete sys;
 }
 
-static cudaError_t shard_alloc(Shard &s, int world) {
+static cudaError_t shard_alloc(Shard &s, int world, bool persist) {
 	const Mat &M = s.M;
 	/* matrix + (sharded) exchange block in ONE allocation */
 	const size_t mat_bytes = (size_t)M.ns * (size_t)M.mp * SBYTES;
@@ -338,6 +364,13 @@ static cudaError_t shard_alloc(Shard &s, int world) {
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_x, (size_t)(M.nw + 1) * 8);
 	if (e == cudaSuccess) e = cudaMalloc(&s.d_slab, (size_t)BS_S * 64 * BS_W * 8);
 	s.d_slab_all = s.d_slab;
+#if SW == 8
+	if (persist && world == 1) {
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_ebuf2, (size_t)M.ns * EBUF_Q * 16);
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_gs, sizeof(GridSync));
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_tpanel, (size_t)(M.nw + 2) * 8);
+	}
+#endif
 	if (world > 1) {
 		s.d_slab_all = nullptr;
 		if (e == cudaSuccess) e = cudaMalloc(&s.d_slab_all, (size_t)world * BS_S * 64 * BS_W * 8);
@@ -442,9 +475,10 @@ extern "C" int gf2b200_system_create(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2
 		h.d_pc[0] = h.d_pc[1] = nullptr;
 		h.d_state = nullptr; h.d_pd = nullptr; h.d_hist_r = nullptr; h.d_hist_pm = nullptr;
 		h.d_ebuf = nullptr; h.d_dp = nullptr; h.d_hist_owner = nullptr;
+		h.d_ebuf2 = nullptr; h.d_gs = nullptr; h.d_tpanel = nullptr;
 		h.xch = nullptr; h.d_pt = nullptr;
 		h.d_x = h.d_slab = h.d_slab_all = nullptr;
-		e = shard_alloc(h, ctx->world);
+		e = shard_alloc(h, ctx->world, ctx->persist != 0);
 	}
 	if (e != cudaSuccess) {
 		int rc = fail(ctx, e == cudaErrorMemoryAllocation ? GF2B200_ENOMEM : GF2B200_ECUDA,
@@ -631,17 +665,41 @@ static int forward_single(gf2b200_system *sys, long long *launches) {
 		}
 		int s0a = w >> SW_SHIFT;
 		k_apply<<<std::min(M.ns - s0a, apply_cap), APPLY_THREADS, 0, st>>>(M, pd, h.d_ebuf, s0a);
-		if (prof) CK(ctx, cudaEventRecord(sys->ev[4 + 2 * w], st));
+		if (prof) CK(ctx, cudaEventRecord(sys->ev[6 + 2 * w], st));
 		k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(M, pd, pc_cur, pc_next, h.d_ebuf, w,
 		                                                     (w + 1) >> SW_SHIFT,
 		                                                     pdn, h.d_state, h.d_hist_r, h.d_hist_pm, colmask_next);
-		if (prof) CK(ctx, cudaEventRecord(sys->ev[5 + 2 * w], st));
+		if (prof) CK(ctx, cudaEventRecord(sys->ev[7 + 2 * w], st));
 		*launches += 2;
 	}
 	k_check<<<grid_for(M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(M, h.d_state);
 	(*launches)++;
 	return GF2B200_OK;
 }
+
+#if SW == 8
+/* forward elimination of a one-shard system as ONE cooperative kernel (gf2b200_persist.cuh) */
+static int forward_single_persist(gf2b200_system *sys, long long *launches) {
+	gf2b200_ctx *ctx = sys->ctx;
+	Shard &h = sys->sh[0];
+	const Mat &M = h.M;
+	cudaStream_t st = ctx->stream;
+	CK(ctx, cudaMemsetAsync(h.d_gs, 0, sizeof(GridSync), st));
+	CK(ctx, cudaMemsetAsync(h.d_tpanel, 0, (size_t)(M.nw + 2) * 8, st));
+	k_extract_pc<<<grid_for(M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(M, 0, h.d_pc[0], 0);
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeCooperative;
+	at[0].val.cooperative = 1;
+	cudaLaunchConfig_t cfg = {dim3(ctx->n_sm), dim3(SWEEP_THREADS), PERSIST_SMEM, st, at, 1};
+	CK(ctx, cudaEventRecord(sys->ev[3], st));
+	CK(ctx, cudaLaunchKernelEx(&cfg, k_forward, M, h.d_pc[0], h.d_pc[1], h.d_ebuf, h.d_ebuf2, h.d_pd, h.d_state,
+	                           h.d_hist_r, h.d_hist_pm, (GridSync *)h.d_gs, h.d_tpanel, 0, M.nw));
+	CK(ctx, cudaEventRecord(sys->ev[4], st));
+	k_check<<<grid_for(M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(M, h.d_state);
+	*launches += 3;
+	return GF2B200_OK;
+}
+#endif
 
 /* forward elimination of a row-sharded system: the per-panel exchange goes through
  * peer memory (gf2b200_dist.cuh); an NCCL context adds the flag waits, a loopback
@@ -680,11 +738,11 @@ static int forward_sharded(gf2b200_system *sys, long long *launches, double *xby
 		for (Shard &h : sys->sh) {
 			k_apply_commit<<<std::min(nsr, apply_cap), APPLY_THREADS, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_ebuf, s0a);
 			const bool ev = prof && li == 0;
-			if (ev) CK(ctx, cudaEventRecord(sys->ev[4 + 2 * w], st));
+			if (ev) CK(ctx, cudaEventRecord(sys->ev[6 + 2 * w], st));
 			k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(h.M, h.d_pd, h.d_pc[w & 1],
 			                                                     h.d_pc[(w + 1) & 1], h.d_ebuf, w,
 			                                                     (w + 1) >> SW_SHIFT, nullptr, nullptr, nullptr, nullptr, 0);
-			if (ev) CK(ctx, cudaEventRecord(sys->ev[5 + 2 * w], st));
+			if (ev) CK(ctx, cudaEventRecord(sys->ev[7 + 2 * w], st));
 			li++;
 		}
 		*launches += 5 * (long long)sys->sh.size();
@@ -735,7 +793,7 @@ extern "C" int gf2b200_system_eliminate(gf2b200_system *sys) {
 	const int nw = sys->sh[0].M.nw, ns = sys->sh[0].M.ns;
 	const bool prof = ctx->profile != 0;
 	const bool sharded = ctx->world > 1;
-	size_t need_ev = 4 + (prof ? 2 * (size_t)nw : 0);
+	size_t need_ev = 6 + (prof ? 2 * (size_t)nw : 0);
 	while (sys->ev.size() < need_ev) {
 		cudaEvent_t e;
 		CK(ctx, cudaEventCreate(&e));
@@ -750,7 +808,16 @@ extern "C" int gf2b200_system_eliminate(gf2b200_system *sys) {
 		CK(ctx, cudaMemsetAsync(h.d_state, 0, sizeof(SolverState), st));
 		CK(ctx, cudaMemsetAsync(h.d_pd, 0, 2 * sizeof(PanelDesc), st));
 	}
-	int rc = sharded ? forward_sharded(sys, &launches, &xbytes) : forward_single(sys, &launches);
+	bool persist = false;
+#if SW == 8
+	persist = !sharded && ctx->persist && sys->sh[0].d_gs;
+#endif
+	int rc;
+	if (sharded) rc = forward_sharded(sys, &launches, &xbytes);
+#if SW == 8
+	else if (persist) rc = forward_single_persist(sys, &launches);
+#endif
+	else rc = forward_single(sys, &launches);
 	if (rc) return rc;
 	CK(ctx, cudaEventRecord(ev_fwd, st));
 	rc = backward(sys, &launches, &xbytes);
@@ -772,7 +839,21 @@ extern "C" int gf2b200_system_eliminate(gf2b200_system *sys) {
 		CK(ctx, cudaMemcpyAsync(h.hist_r.data(), h.d_hist_r, (size_t)nw * 8, cudaMemcpyDeviceToHost, st));
 		CK(ctx, cudaMemcpyAsync(&hs[l], h.d_state, sizeof(SolverState), cudaMemcpyDeviceToHost, st));
 	}
+	std::vector<unsigned long long> tpanel;
+#if SW == 8
+	GridSync hgs;
+	memset(&hgs, 0, sizeof hgs);
+	if (persist) {
+		tpanel.resize((size_t)nw + 2);
+		CK(ctx, cudaMemcpyAsync(tpanel.data(), sys->sh[0].d_tpanel, ((size_t)nw + 2) * 8, cudaMemcpyDeviceToHost, st));
+		CK(ctx, cudaMemcpyAsync(&hgs, sys->sh[0].d_gs, sizeof hgs, cudaMemcpyDeviceToHost, st));
+	}
+#endif
 	CK(ctx, cudaStreamSynchronize(st));
+#if SW == 8
+	if (persist && hgs.fault)
+		return fail(ctx, GF2B200_ECUDA, "k_forward: a grid-wide wait timed out (the persistent kernel gave up)");
+#endif
 	sys->rank = hs[0].r;
 	int bad = 0;
 	for (const SolverState &s : hs) {
@@ -828,8 +909,22 @@ extern "C" int gf2b200_system_eliminate(gf2b200_system *sys) {
 			double bytes = 2.0 * (double)(h.M.m - r1) * (double)SBYTES * (double)(ns - ((w + 1) >> SW_SHIFT));
 			S.sweep_bytes += bytes;
 			S.sweep_launches++;
-			if (prof && l == 0) {
-				CK(ctx, cudaEventElapsedTime(&ms, sys->ev[4 + 2 * w], sys->ev[5 + 2 * w]));
+			if (persist) {
+				/* per-panel wall time inside the one kernel (globaltimer at the top of every
+				 * panel): sweep + look-ahead search + apply + grid barrier of that panel */
+				int wq = w + 1;
+				while (wq <= nw && !tpanel[wq]) wq++;
+				if (wq <= nw && tpanel[w]) {
+					const double pms = (double)(tpanel[wq] - tpanel[w]) * 1e-6;
+					S.sweep_bytes_timed += bytes;
+					S.sweep_launches_timed++;
+					if (pms > S.ms_sweep_max) {
+						S.ms_sweep_max = pms;
+						S.sweep_bytes_max = bytes;
+					}
+				}
+			} else if (prof && l == 0) {
+				CK(ctx, cudaEventElapsedTime(&ms, sys->ev[6 + 2 * w], sys->ev[7 + 2 * w]));
 				S.ms_sweep += ms;
 				S.sweep_bytes_timed += bytes;
 				S.sweep_launches_timed++;
@@ -839,6 +934,12 @@ extern "C" int gf2b200_system_eliminate(gf2b200_system *sys) {
 				}
 			}
 		}
+	}
+	if (persist) {
+		/* one launch did all the sweeps: its duration is the denominator of the roofline */
+		CK(ctx, cudaEventElapsedTime(&ms, sys->ev[3], sys->ev[4]));
+		S.ms_sweep = ms;
+		S.forward_kernel_launches = 1;
 	}
 	return GF2B200_OK;
 }

@@ -291,7 +291,8 @@ __device__ __forceinline__ void select_scan(SelectSmem &S, const u64 *__restrict
 		u64 pm = S.pm;
 		if (pm == colmask) break;
 		long long i = base + tid;
-		u64 v = (i < m) ? (pc[i] & colmask) : 0;
+		/* ld.cg: inside the persistent kernel another SM wrote these words moments ago */
+		u64 v = (i < m) ? (__ldcg(pc + i) & colmask) : 0;
 		u64 tv = 0;
 		u64 x = v & pm;
 		while (x) {
@@ -391,13 +392,13 @@ __device__ __forceinline__ void select_finalize(SelectSmem &S, u64 *__restrict__
 	u64 tmpv[2];
 	for (int h = 0; h < 2; h++) {
 		int q = lane + 32 * h;
-		tmpv[h] = (q < ndis) ? pc[S.mv_src[q]] : 0;
+		tmpv[h] = (q < ndis) ? __ldcg(pc + S.mv_src[q]) : 0;
 	}
 	__syncwarp();
 	for (int h = 0; h < 2; h++) {
 		int q = lane + 32 * h;
 		if (q < ndis) {
-			pc[S.mv_dst[q]] = tmpv[h];
+			__stcg(pc + S.mv_dst[q], tmpv[h]);
 			pd->mv_src[q] = S.mv_src[q];
 			pd->mv_dst[q] = S.mv_dst[q];
 		}

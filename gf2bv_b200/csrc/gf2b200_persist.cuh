@@ -1,0 +1,417 @@
+/*
+ * gf2b200_persist.cuh -- k_forward: the whole forward elimination of a one-GPU system as
+ * ONE persistent cooperative kernel (1 CTA of 1024 threads per SM, every CTA resident).
+ *
+ * What it replaces: the per-panel launch chain k_select -> k_apply -> k_sweep of
+ * gf2b200_kernels.cuh (still used by the row-sharded path and by 128-byte-strip builds).
+ * Same arithmetic, same tables, same bit-exact result (M4RI's _mzd_pluq semantics,
+ * reference gf2bv/_internal.c:433) -- what changes is WHERE the per-panel
+ * fixed cost goes.  Measured in round 1 (profiles/r01c_launches.md):
+ * ~30 us per panel outside the streaming part of the sweep (three launches and their
+ * gaps, k_apply 7.9 us, a no-op k_select 2.3 us, launch ramp and drain), 10 % of a solve at
+ * n = 131072 and two thirds of it at n = 32768.  Here one panel is
+ *
+ *   sweep(w)      every CTA streams its contiguous range of work units (a unit = one
+ *                 64-byte strip x 1024 rows), exactly as k_sweep does;
+ *   search(w+1)   the CTA that owns unit 0 (strip of word w+1, first 1024 active rows)
+ *                 searches those rows for the next panel's pivots as soon as it has
+ *                 swept them (as k_sweep's fused search does) and publishes the result
+ *                 with a release store; the other 147 CTAs keep streaming;
+ *   apply(w+1)    every CTA, once its own range is done, builds E = TB * Sel for the
+ *                 strips whose first-1024-rows unit IT swept (so the rows it reads are
+ *                 rows it wrote; no other CTA touches them in this panel), stores the
+ *                 pivot rows in place, moves the displaced rows and writes the E tile
+ *                 of the strip into the OTHER half of the double-buffered ebuf;
+ *   grid barrier  one per panel.
+ *
+ * When the first 1024 active rows do not settle the next panel (rank-deficient or
+ * sparse systems) the panel ends with the slow path: barrier, full scan of the panel
+ * column by CTA 0, barrier, apply spread over all CTAs, barrier.
+ *
+ * Memory model: everything another CTA wrote during this kernel is read with ld.cg
+ * (L2) or an acquire load, never through L1 or the non-coherent path; the E tile still
+ * arrives by TMA bulk copy (L2 -> shared memory) after a proxy fence.  Every wait has
+ * a time-out that raises GridSync::fault and makes all CTAs leave: a logic error ends
+ * in an error code, not in a hung GPU.
+ */
+#pragma once
+#include "gf2b200_kernels.cuh"
+
+#if SW == 8
+namespace gf2b200 {
+
+struct GridSync {
+	unsigned count, gen; /* grid barrier: arrivals, generation */
+	unsigned sel_flag;   /* panel index + 1 whose description the look-ahead search made final */
+	unsigned need_full;  /* panel index + 1 for which the first 1024 rows were not enough */
+	int fault;           /* a wait timed out */
+	int done_w;          /* panels finished (diagnostic) */
+	unsigned pad[2];
+};
+
+/* How the sweep reads a row's coefficient (the panel word pc_cur[row]):
+ *   0  ld.cg (L2 only)
+ *   1  plain ld.global (L1-cached).  Safe inside the kernel: the words were written before
+ *      the last grid barrier, whose acquire invalidates this SM's L1 (PTX memory model:
+ *      weak loads after an acquire observe what happened before the release); never the
+ *      non-coherent path (ld.global.nc is outside the model).
+ * PERSIST_UNCOND_LOADS 1: the row loads do not wait for the coefficient (rows whose
+ * coefficient turns out to be zero are read for nothing and not written). */
+#ifndef PERSIST_CF_LOAD
+#define PERSIST_CF_LOAD 1
+#endif
+#ifndef PERSIST_UNCOND_LOADS
+#define PERSIST_UNCOND_LOADS 0
+#endif
+#ifndef PERSIST_TIMEOUT_NS
+#define PERSIST_TIMEOUT_NS 20000000000ULL
+#endif
+
+#ifndef GF2_EMU
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+	unsigned v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+/* generic-proxy writes (other CTAs' st.global, made visible by the acquire before this)
+ * before the async-proxy read of the bulk copy that follows */
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+/* a plain (weak, L1-allocating) global load the compiler can neither drop nor turn into ld.global.nc */
+__device__ __forceinline__ u64 ld_weak_u64(const u64 *p) {
+	u64 v;
+	asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p));
+	return v;
+}
+#else
+__device__ __forceinline__ u64 ld_weak_u64(const u64 *p) { return *p; }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ unsigned long long gtimer_ns() { return (unsigned long long)(emu_now_ms() * 1e6); }
+__device__ __forceinline__ void fence_proxy_async() {}
+#endif
+
+/* one thread: wait until *p - target >= 0 (flags only grow) or the other flag does */
+__device__ __forceinline__ bool persist_wait(const unsigned *p, unsigned target, const unsigned *alt, GridSync *gs) {
+	const unsigned long long t0 = gtimer_ns();
+	unsigned it = 0;
+	for (;;) {
+		if ((int)(ld_acquire_gpu(p) - target) >= 0) return true;
+		if (alt && (int)(ld_acquire_gpu(alt) - target) >= 0) return true;
+		if ((++it & 31) == 0) {
+			if (*(volatile int *)&gs->fault) return false;
+			if (gtimer_ns() - t0 > PERSIST_TIMEOUT_NS) {
+				atomicOr(&gs->fault, 1);
+				return false;
+			}
+		}
+		__nanosleep(40);
+	}
+}
+
+/* all threads of all CTAs; false after a fault (uniform over the CTA) */
+__device__ __forceinline__ bool grid_barrier(GridSync *gs, int *s_ok) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		const unsigned g = ld_acquire_gpu(&gs->gen);
+		bool ok = true;
+		if (atomicAdd(&gs->count, 1u) == gridDim.x - 1) {
+			atomicExch(&gs->count, 0u);
+			__threadfence();
+			st_release_gpu(&gs->gen, g + 1);
+		} else {
+			ok = persist_wait(&gs->gen, g + 1, nullptr, gs);
+		}
+		__threadfence();
+		*s_ok = (ok && !*(volatile int *)&gs->fault) ? 1 : 0;
+	}
+	__syncthreads();
+	return *s_ok != 0;
+}
+
+/* Shared-memory image of the panel description an apply needs. */
+struct ApplySmem {
+	uint4 Sel[4][64][SQ]; /* four strips at a time, 256 threads each */
+	uint4 Dis[4][64][SQ];
+	u64 TB[64];
+	int sel[64], src[64], dst[64];
+	int k, nmove;
+	long long r;
+	u64 pm;
+};
+
+/* E = TB * Sel for the strips list(i), i in [0, count): rows r..r+k-1 <- E (pivot rows),
+ * displaced rows -> vacated positions, E tile -> ebuf_dst.  All SWEEP_THREADS threads.
+ * The description is read with ld.cg: another CTA may have written it in this kernel. */
+template <typename StripOf>
+__device__ __forceinline__ void persist_apply(const Mat &M, const PanelDesc *pdn, uint4 *__restrict__ ebuf_dst,
+                                              ApplySmem &A, int count, StripOf strip_of) {
+	const int tid = threadIdx.x;
+	if (tid < 64) {
+		A.TB[tid] = __ldcg(&pdn->TB[tid]);
+		A.sel[tid] = __ldcg(&pdn->sel[tid]);
+		A.src[tid] = __ldcg(&pdn->mv_src[tid]);
+		A.dst[tid] = __ldcg(&pdn->mv_dst[tid]);
+	}
+	if (tid == 0) {
+		A.k = __ldcg(&pdn->k);
+		A.nmove = __ldcg(&pdn->nmove);
+		A.r = __ldcg(&pdn->r);
+		A.pm = __ldcg(&pdn->pm);
+	}
+	__syncthreads();
+	const int k = A.k, nmove = A.nmove;
+	if (k == 0) return;
+	const int g = tid >> 8, t8 = tid & 255, rr = t8 / SQ, ch = t8 % SQ;
+	const u64 pm = A.pm;
+	const long long erow = A.r + __popcll(pm & ((1ULL << rr) - 1));
+	const bool ispiv = (pm >> rr) & 1;
+	uint4 *mb = reinterpret_cast<uint4 *>(M.base);
+	const uint4 z = make_uint4(0, 0, 0, 0);
+	for (int i0 = 0; i0 < count; i0 += 4) {
+		const int i = i0 + g;
+		const bool on = i < count;
+		const int s = on ? strip_of(i) : 0;
+		const long long sb = (long long)s * M.mp;
+		if (on) {
+			A.Sel[g][rr][ch] = (rr < k) ? __ldcg(mb + (sb + A.sel[rr]) * SQ + ch) : z;
+			if (rr < nmove) A.Dis[g][rr][ch] = __ldcg(mb + (sb + A.src[rr]) * SQ + ch);
+		}
+		__syncthreads();
+		if (on) {
+			uint4 acc = z;
+			u64 t = A.TB[rr];
+			while (t) {
+				const int l = __ffsll((long long)t) - 1;
+				t &= t - 1;
+				xor4(acc, A.Sel[g][l][ch]);
+			}
+			__stcg(ebuf_dst + (long long)s * EBUF_Q + rr * SQ + ch, acc);
+			if (ispiv) __stcg(mb + (sb + erow) * SQ + ch, acc);
+			if (rr < nmove) __stcg(mb + (sb + A.dst[rr]) * SQ + ch, A.Dis[g][rr][ch]);
+		}
+		__syncthreads();
+	}
+}
+
+#define PERSIST_CTRL_BYTES 64
+#define PERSIST_SMEM (SWEEP_LINES * 128 + SWEEP_SCRATCH_BYTES + 16 + PERSIST_CTRL_BYTES)
+static_assert(sizeof(ApplySmem) <= SWEEP_LINES * 128, "the apply scratch aliases the (dead) tables");
+
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2, SolverState *st,
+          long long *hist_r, u64 *hist_pm, GridSync *gs, unsigned long long *t_panel, int w_begin, int w_end) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	uint4 *TD = reinterpret_cast<uint4 *>(smem_raw);
+	uint4 *E = TD + SWEEP_LINES * 8;
+	uint4 *P = E + EBUF_Q;
+	u64 *bar = reinterpret_cast<u64 *>(smem_raw + SWEEP_LINES * 128 + SWEEP_SCRATCH_BYTES);
+	int *s_ok = reinterpret_cast<int *>(smem_raw + SWEEP_LINES * 128 + SWEEP_SCRATCH_BYTES + 16);
+	int *s_state = s_ok + 1; /* 1: description of the next panel is final, 2: needs the full scan, 0: fault */
+	SelectSmem &S = *reinterpret_cast<SelectSmem *>(smem_raw + SWEEP_LINES * 128);
+	ApplySmem &AP = *reinterpret_cast<ApplySmem *>(smem_raw);
+
+	const int tid = threadIdx.x;
+	const int G = gridDim.x;
+	const long long m = M.m;
+	const int nw = M.nw;
+	uint4 *mb = reinterpret_cast<uint4 *>(M.base);
+	if (tid == 0) {
+		mbar_init(bar, 1);
+		mbar_init_fence();
+	}
+	__syncthreads();
+	unsigned phase = 0;
+	const int ch = tid % SQ, rl = tid / SQ;
+	const int h = rl & 1;
+	const unsigned char *Tbe = reinterpret_cast<const unsigned char *>(TD + 4 * h + ch);
+	const unsigned char *Tbo = reinterpret_cast<const unsigned char *>(TD + 4 * (1 - h) + ch);
+	const unsigned bsel = h ? 0x2301u : 0x3210u;
+
+	for (int w = w_begin; w < w_end; ++w) {
+		u64 *pc_cur = (w & 1) ? pc1 : pc0, *pc_next = (w & 1) ? pc0 : pc1;
+		const uint4 *ebuf = (w & 1) ? ebuf1 : ebuf0;
+		uint4 *ebuf_next = (w & 1) ? ebuf0 : ebuf1;
+		PanelDesc *pd = pd2 + (w & 1), *pdn = pd2 + ((w + 1) & 1);
+		if (blockIdx.x == 0 && tid == 0) t_panel[w] = gtimer_ns();
+
+		/* ---- slow path: nobody settled this panel ahead of time ---------------- */
+		if (*(volatile int *)&pd->valid != w + 1) {
+			u64 colmask = ~0ULL;
+			if (w == nw - 1 && (M.n & 63)) colmask = (1ULL << (M.n & 63)) - 1;
+			if (blockIdx.x == 0) {
+				const long long r = *(volatile long long *)&st->r;
+				select_init(S);
+				__syncthreads();
+				select_scan(S, pc_cur, r, m, colmask);
+				if (tid < 32) select_finalize(S, pc_cur, w, r, st, pd, hist_r, hist_pm);
+			}
+			if (!grid_barrier(gs, s_ok)) return;
+			const int s0a = w >> SW_SHIFT;
+			const int mine = (M.ns - s0a - (int)blockIdx.x + G - 1) / G; /* strips s0a + b + i*G */
+			persist_apply(M, pd, const_cast<uint4 *>(ebuf), AP, mine > 0 ? mine : 0,
+			              [&](int i) { return s0a + (int)blockIdx.x + i * G; });
+			if (!grid_barrier(gs, s_ok)) return;
+		}
+
+		const int k = *(volatile int *)&pd->k;
+		const long long r1 = *(volatile long long *)&pd->r1;
+		const u64 pm = *(volatile u64 *)&pd->pm;
+		const int wn = w + 1;
+		const bool has_next = wn < nw;
+		if (r1 >= m) {
+			/* every row is an echelon row: the remaining panels have no pivots */
+			if (blockIdx.x == 0)
+				for (int x = wn + tid; x < nw; x += SWEEP_THREADS) {
+					hist_r[x] = r1;
+					hist_pm[x] = 0;
+				}
+			break;
+		}
+		if (k == 0) {
+			/* nothing to eliminate: hand the next word column to the (slow-path) search */
+			for (long long i = r1 + blockIdx.x * (long long)SWEEP_THREADS + tid; i < m; i += (long long)G * SWEEP_THREADS)
+				pc_next[i] = __ldcg(M.base + widx(M, i, wn));
+			if (!grid_barrier(gs, s_ok)) return;
+			continue;
+		}
+
+		/* ---- sweep(w): rows [r1, m) x strips [s0, ns) ---------------------------- */
+		const int s0 = wn >> SW_SHIFT;
+		const long long base8 = r1 & ~7LL; /* chunks start on 512-byte boundaries of the strip */
+		const long long nchunks = (m - base8 + SWEEP_RU - 1) / SWEEP_RU;
+		const long long units = (long long)(M.ns - s0) * nchunks;
+		const long long vpad = has_next ? max(0LL, min((long long)SWEEP_SEL_PAD, units / G - 1)) : 0;
+		const long long vunits = units + vpad;
+		const long long u0 = max(0LL, vunits * blockIdx.x / G - vpad);
+		const long long u1 = vunits * (blockIdx.x + 1) / G - vpad;
+		const int nch = (wn & (SW - 1)) >> 1;
+		u64 colmask_next = ~0ULL;
+		if (wn == nw - 1 && (M.n & 63)) colmask_next = (1ULL << (M.n & 63)) - 1;
+		if (u0 < u1) {
+			int cur = -1, fetched = -1;
+			const int s_last = s0 + (int)((u1 - 1) / nchunks);
+			for (long long u = u0; u < u1; ++u) {
+				const int s = s0 + (int)(u / nchunks);
+				const long long chunk = u % nchunks;
+				if (s != cur) {
+					__syncthreads(); /* everyone is done with the previous tables */
+					if (fetched != s && tid == 0) {
+						fence_proxy_async();
+						mbar_expect_tx(bar, EBUF_Q * 16);
+						tma_bulk_g2s(E, ebuf + (long long)s * EBUF_Q, EBUF_Q * 16, bar);
+					}
+					mbar_wait(bar, phase);
+					phase ^= 1;
+					const bool more = SWEEP_EARLY_TILE && (s < s_last) && !(has_next && u == 0);
+					if (more && tid == 0) fence_proxy_async();
+					sweep_build_tables(TD, P, E, tid, more ? ebuf + (long long)(s + 1) * EBUF_Q : nullptr, bar);
+					fetched = more ? s + 1 : -1;
+					cur = s;
+				}
+				const long long row0 = base8 + chunk * SWEEP_RU + rl;
+				const bool force = (s == s0);
+				uint4 *p = mb + ((long long)s * M.mp + row0) * SQ + ch;
+				u64 cf[SWEEP_U];
+				uint4 d[SWEEP_U];
+				bool act[SWEEP_U];
+#pragma unroll
+				for (int q = 0; q < SWEEP_U; q++) {
+					const long long row = row0 + (SWEEP_THREADS / SQ) * q;
+#if PERSIST_CF_LOAD == 0
+					cf[q] = (row >= r1 && row < m) ? (__ldcg(pc_cur + row) & pm) : 0;
+#else
+					cf[q] = (row >= r1 && row < m) ? (ld_weak_u64(pc_cur + row) & pm) : 0;
+#endif
+				}
+#pragma unroll
+				for (int q = 0; q < SWEEP_U; q++) {
+					const long long row = row0 + (SWEEP_THREADS / SQ) * q;
+#if PERSIST_UNCOND_LOADS
+					if (row >= r1 && row < m) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ);
+					act[q] = (row >= r1 && row < m) && (cf[q] != 0 || force);
+#else
+					act[q] = (row >= r1 && row < m) && (cf[q] != 0 || force);
+					if (act[q]) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ);
+#endif
+				}
+#pragma unroll
+				for (int q = 0; q < SWEEP_U; q++) {
+					if (!act[q]) continue;
+					uint4 v = d[q];
+					const unsigned lo = __byte_perm((unsigned)cf[q], 0, bsel);
+					const unsigned hi = __byte_perm((unsigned)(cf[q] >> 32), 0, bsel);
+#define TLOOK(base, off) (*reinterpret_cast<const uint4 *>((base) + (off)))
+					xor4(v, TLOOK(Tbe, 0 * 32768 + ((lo << 7) & 0x7F80u)));
+					xor4(v, TLOOK(Tbo, 0 * 32768 + ((lo >> 1) & 0x7F80u)));
+					xor4(v, TLOOK(Tbe, 1 * 32768 + ((lo >> 9) & 0x7F80u)));
+					xor4(v, TLOOK(Tbo, 1 * 32768 + ((lo >> 17) & 0x7F80u)));
+					xor4(v, TLOOK(Tbe, 2 * 32768 + ((hi << 7) & 0x7F80u)));
+					xor4(v, TLOOK(Tbo, 2 * 32768 + ((hi >> 1) & 0x7F80u)));
+					xor4(v, TLOOK(Tbe, 3 * 32768 + ((hi >> 9) & 0x7F80u)));
+					xor4(v, TLOOK(Tbo, 3 * 32768 + ((hi >> 17) & 0x7F80u)));
+#undef TLOOK
+					__stcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ, v);
+					if (force && ch == nch) {
+						const long long row = row0 + (SWEEP_THREADS / SQ) * q;
+						__stcg(pc_next + row, (wn & 1) ? (((u64)v.w << 32) | v.z) : (((u64)v.y << 32) | v.x));
+					}
+				}
+				if (has_next && u == 0) {
+					/* look-ahead: this CTA just produced word w+1 of the first active rows; search
+					 * them for the next panel's pivots while the other SMs keep streaming */
+					__threadfence_block();
+					__syncthreads();
+					select_init(S);
+					__syncthreads();
+					const long long lim = min(m, base8 + (long long)SWEEP_RU);
+					select_scan(S, pc_next, r1, lim, colmask_next);
+					if (tid < 32) {
+						const bool final_ = (S.pm == colmask_next || lim == m);
+						if (final_) select_finalize(S, pc_next, wn, r1, st, pdn, hist_r, hist_pm);
+						__syncwarp();
+						if (tid == 0) {
+							__threadfence();
+							st_release_gpu(final_ ? &gs->sel_flag : &gs->need_full, (unsigned)wn + 1);
+						}
+					}
+					__syncthreads();
+				}
+			}
+		}
+
+		/* ---- apply(w+1) for the strips whose first-rows unit this CTA swept ------- */
+		if (has_next) {
+			__syncthreads(); /* the tables are dead: their space is the apply scratch */
+			if (tid == 0) {
+				int state = 0;
+				if (persist_wait(&gs->sel_flag, (unsigned)wn + 1, &gs->need_full, gs))
+					state = ((int)(ld_acquire_gpu(&gs->sel_flag) - ((unsigned)wn + 1)) >= 0) ? 1 : 2;
+				__threadfence();
+				*s_state = state;
+			}
+			__syncthreads();
+			const int state = *s_state;
+			if (state == 0) return;
+			if (state == 1 && u0 < u1) {
+				const long long sa = (u0 + nchunks - 1) / nchunks, sb = (u1 - 1) / nchunks; /* strips (relative) whose chunk 0 is mine */
+				const int cnt = (int)(sb - sa + 1);
+				persist_apply(M, pdn, ebuf_next, AP, cnt > 0 ? cnt : 0, [&](int i) { return s0 + (int)sa + i; });
+			}
+		}
+		if (blockIdx.x == 0 && tid == 0) gs->done_w = wn;
+		if (!grid_barrier(gs, s_ok)) return;
+	}
+	if (blockIdx.x == 0 && tid == 0) t_panel[w_end] = gtimer_ns();
+}
+
+} /* namespace gf2b200 */
+#endif /* SW == 8 */

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GF2B200_ABI_VERSION 1
+#define GF2B200_ABI_VERSION 2
 
 #define GF2B200_OK 0
 #define GF2B200_INCONSISTENT 1 /* result.status only: system has no solution (-> None) */
@@ -72,6 +72,10 @@ typedef struct {
 	double sweep_bytes_max;
 	double sweep_bytes_timed;     /* profile mode: algorithmic bytes of the launches in ms_sweep */
 	int64_t sweep_launches_timed; /* (a loopback context times its first shard only) */
+	int64_t forward_kernel_launches; /* 1: the forward elimination ran as ONE persistent kernel (k_forward);
+	                                  * ms_sweep is then that kernel's duration (always measured),
+	                                  * sweep_launches counts its panels with work and ms_sweep_max /
+	                                  * sweep_bytes_max describe its longest panel.  0: per-panel launches */
 } gf2b200_stats;
 
 int gf2b200_abi_version(void);

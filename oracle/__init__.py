@@ -95,6 +95,8 @@ def lib() -> ctypes.CDLL:
         _lib.gf2o_result_free.argtypes = [ctypes.POINTER(_Result)]
         _lib.gf2o_result_free.restype = None
         _lib.gf2o_threads.restype = ctypes.c_int
+        _lib.gf2o_set_threads.argtypes = [ctypes.c_int]
+        _lib.gf2o_set_threads.restype = None
         _lib.gf2o_synth.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, u64p, u64p]
         _lib.gf2o_synth.restype = None
         _lib.gf2o_synth_xstar.argtypes = [ctypes.c_int64, ctypes.c_uint64, u64p]
@@ -175,6 +177,12 @@ def residual(A: np.ndarray, b: Optional[np.ndarray], n: int, x: np.ndarray) -> i
 
 def threads() -> int:
     return int(lib().gf2o_threads())
+
+
+def set_threads(n: int) -> None:
+    """Fix the OpenMP thread count of the tier-2 port (bench.py: torchrun exports
+    OMP_NUM_THREADS=1, which must not apply to the CPU baseline)."""
+    lib().gf2o_set_threads(int(n))
 
 
 # --------------------------------------------------------------------------

@@ -71,7 +71,7 @@ void gf2o_result_free(gf2o_result *r) {
 
 int gf2o_threads(void) {
 #ifdef _OPENMP
-	return omp_get_max_threads();
+	return omp_get_max_threads(); /* after gf2o_set_threads(n): n */
 #else
 	return 1;
 #endif
@@ -187,17 +187,40 @@ int gf2o_solve_schoolbook(const uint64_t *A, const uint64_t *b, int64_t m, int64
  * fully reduced inside their own 64-column panel; back-substitution then gives
  * the particular solution and (mode 1) one kernel vector per free column.
  * ------------------------------------------------------------------------- */
-#define CHUNK 64 /* words per column chunk: 8 tables x 256 x 512 B = 1 MiB */
+/* Column-chunk width of the sweep (64-bit words).  Chosen per solve so that there are
+ * at least ~3 chunks per thread at any n (the first version used a fixed 64 words: at
+ * n = 16384 that left 5 chunks for 16 cores) and so that a thread's eight 256-entry
+ * tables (8 x 256 x cw x 8 B) stay inside its L2. */
+#define CHUNK_MAX 32
+
+static int g_threads_override = 0;
+
+/* bench.py sets the thread count explicitly (torchrun exports OMP_NUM_THREADS=1) */
+void gf2o_set_threads(int n) {
+	g_threads_override = n > 0 ? n : 0;
+#ifdef _OPENMP
+	if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
+static int64_t chunk_words(int64_t W, int nthr) {
+	int64_t cw = (W + 3 * (int64_t)nthr - 1) / (3 * (int64_t)nthr);
+	cw = (cw + 7) / 8 * 8;
+	if (cw < 8) cw = 8;
+	if (cw > CHUNK_MAX) cw = CHUNK_MAX;
+	return cw;
+}
 
 static int forward_m4rm(uint64_t *M, int64_t m, int64_t n, int64_t W, int64_t *piv,
                         int64_t *rank_out) {
 	int64_t nw = (n + 63) / 64;
 	int64_t r = 0;
 	int nthr = gf2o_threads();
+	const int64_t CH = chunk_words(W, nthr);
 	uint64_t *E = (uint64_t *)malloc((size_t)64 * (size_t)W * 8); /* reduced pivot rows */
 	uint64_t *tmp = (uint64_t *)malloc((size_t)W * 8);
 	uint64_t *coef = (uint64_t *)malloc((size_t)(m ? m : 1) * 8);
-	uint64_t *T = (uint64_t *)malloc((size_t)nthr * 8 * 256 * CHUNK * 8);
+	uint64_t *T = (uint64_t *)aligned_alloc(64, (size_t)nthr * 8 * 256 * CH * 8);
 	if (!E || !tmp || !coef || !T) { free(E); free(tmp); free(coef); free(T); return GF2O_ENOMEM; }
 	for (int64_t w = 0; w < nw && r < m; w++) {
 		uint64_t colmask = ~0ULL;
@@ -233,6 +256,7 @@ static int forward_m4rm(uint64_t *M, int64_t m, int64_t n, int64_t W, int64_t *p
 		for (int l = 0; l < k; l++) order[__builtin_popcountll(pm & ((1ULL << pcol[l]) - 1))] = l;
 		for (int c = 0; c < 64; c++) slot_of_bit[c] = -1;
 		/* 3. E_j = XOR of the originals named by t[] (words w..W-1) */
+#pragma omp parallel for schedule(static) if (W - w > 512)
 		for (int j = 0; j < k; j++) {
 			uint64_t *e = E + (int64_t)j * W;
 			memset(e + w, 0, (size_t)(W - w) * 8);
@@ -242,6 +266,8 @@ static int forward_m4rm(uint64_t *M, int64_t m, int64_t n, int64_t W, int64_t *p
 				const uint64_t *src = M + sel[l] * W;
 				for (int64_t x = w; x < W; x++) e[x] ^= src[x];
 			}
+		}
+		for (int j = 0; j < k; j++) {
 			slot_of_bit[pcol[order[j]]] = j;
 			piv[r + j] = w * 64 + pcol[order[j]];
 		}
@@ -264,8 +290,19 @@ static int forward_m4rm(uint64_t *M, int64_t m, int64_t n, int64_t W, int64_t *p
 		}
 		int64_t r1 = r + k;
 		/* 5. sweep rows r1..m-1: row ^= sum_j coef_j E_j, coef = raw panel word
-		 *    (E is RREF on the pivot columns so no sequential dependency) */
+		 *    (E is RREF on the pivot columns so no sequential dependency).
+		 *    Work items = (column chunk) x (row block), dealt out dynamically, so every
+		 *    core has work at any n; a thread rebuilds its tables only when it moves
+		 *    to another column chunk. */
+#pragma omp parallel for schedule(static) if (m - r1 > 4096)
 		for (int64_t i = r1; i < m; i++) coef[i] = M[i * W + w] & pm;
+		const int64_t nchunk = (W - w + CH - 1) / CH;
+		const int64_t rows = m - r1;
+		int64_t rblocks = 1;
+		if (nchunk < 3 * (int64_t)nthr) rblocks = (3 * (int64_t)nthr + nchunk - 1) / nchunk;
+		if (rblocks > (rows + 255) / 256) rblocks = (rows + 255) / 256;
+		if (rblocks < 1) rblocks = 1;
+		const int64_t rb = (rows + rblocks - 1) / rblocks;
 #pragma omp parallel
 		{
 #ifdef _OPENMP
@@ -273,37 +310,44 @@ static int forward_m4rm(uint64_t *M, int64_t m, int64_t n, int64_t W, int64_t *p
 #else
 			int tid = 0;
 #endif
-			uint64_t *Tt = T + (size_t)tid * 8 * 256 * CHUNK;
+			uint64_t *Tt = T + (size_t)tid * 8 * 256 * CH;
+			int64_t built = -1;
 #pragma omp for schedule(dynamic, 1)
-			for (int64_t c0 = w; c0 < W; c0 += CHUNK) {
-				int64_t cw = (W - c0 < CHUNK) ? (W - c0) : CHUNK;
-				for (int g = 0; g < 8; g++) {
-					uint64_t *Tg = Tt + (size_t)g * 256 * CHUNK;
-					memset(Tg, 0, (size_t)cw * 8);
-					for (int idx = 1; idx < 256; idx++) {
-						int s = slot_of_bit[g * 8 + __builtin_ctz(idx)];
-						uint64_t *dst = Tg + (size_t)idx * CHUNK;
-						const uint64_t *pv = Tg + (size_t)(idx & (idx - 1)) * CHUNK;
-						if (s < 0) {
-							memcpy(dst, pv, (size_t)cw * 8);
-						} else {
-							const uint64_t *e = E + (int64_t)s * W + c0;
-							for (int64_t x = 0; x < cw; x++) dst[x] = pv[x] ^ e[x];
+			for (int64_t item = 0; item < nchunk * rblocks; item++) {
+				const int64_t ci = item / rblocks, bi = item - ci * rblocks;
+				const int64_t c0 = w + ci * CH;
+				const int64_t cw = (W - c0 < CH) ? (W - c0) : CH;
+				if (built != ci) {
+					for (int g = 0; g < 8; g++) {
+						uint64_t *Tg = Tt + (size_t)g * 256 * CH;
+						memset(Tg, 0, (size_t)cw * 8);
+						for (int idx = 1; idx < 256; idx++) {
+							int s = slot_of_bit[g * 8 + __builtin_ctz(idx)];
+							uint64_t *dst = Tg + (size_t)idx * CH;
+							const uint64_t *pv = Tg + (size_t)(idx & (idx - 1)) * CH;
+							if (s < 0) {
+								memcpy(dst, pv, (size_t)cw * 8);
+							} else {
+								const uint64_t *e = E + (int64_t)s * W + c0;
+								for (int64_t x = 0; x < cw; x++) dst[x] = pv[x] ^ e[x];
+							}
 						}
 					}
+					built = ci;
 				}
-				for (int64_t i = r1; i < m; i++) {
+				const int64_t i0 = r1 + bi * rb, i1 = (i0 + rb < m) ? i0 + rb : m;
+				for (int64_t i = i0; i < i1; i++) {
 					uint64_t cf = coef[i];
 					if (!cf) continue;
-					uint64_t *row = M + i * W + c0;
-					const uint64_t *t0 = Tt + ((size_t)0 * 256 + (cf & 255)) * CHUNK;
-					const uint64_t *t1 = Tt + ((size_t)1 * 256 + ((cf >> 8) & 255)) * CHUNK;
-					const uint64_t *t2 = Tt + ((size_t)2 * 256 + ((cf >> 16) & 255)) * CHUNK;
-					const uint64_t *t3 = Tt + ((size_t)3 * 256 + ((cf >> 24) & 255)) * CHUNK;
-					const uint64_t *t4 = Tt + ((size_t)4 * 256 + ((cf >> 32) & 255)) * CHUNK;
-					const uint64_t *t5 = Tt + ((size_t)5 * 256 + ((cf >> 40) & 255)) * CHUNK;
-					const uint64_t *t6 = Tt + ((size_t)6 * 256 + ((cf >> 48) & 255)) * CHUNK;
-					const uint64_t *t7 = Tt + ((size_t)7 * 256 + ((cf >> 56) & 255)) * CHUNK;
+					uint64_t *restrict row = M + i * W + c0;
+					const uint64_t *restrict t0 = Tt + ((size_t)0 * 256 + (cf & 255)) * CH;
+					const uint64_t *restrict t1 = Tt + ((size_t)1 * 256 + ((cf >> 8) & 255)) * CH;
+					const uint64_t *restrict t2 = Tt + ((size_t)2 * 256 + ((cf >> 16) & 255)) * CH;
+					const uint64_t *restrict t3 = Tt + ((size_t)3 * 256 + ((cf >> 24) & 255)) * CH;
+					const uint64_t *restrict t4 = Tt + ((size_t)4 * 256 + ((cf >> 32) & 255)) * CH;
+					const uint64_t *restrict t5 = Tt + ((size_t)5 * 256 + ((cf >> 40) & 255)) * CH;
+					const uint64_t *restrict t6 = Tt + ((size_t)6 * 256 + ((cf >> 48) & 255)) * CH;
+					const uint64_t *restrict t7 = Tt + ((size_t)7 * 256 + ((cf >> 56) & 255)) * CH;
 					for (int64_t x = 0; x < cw; x++)
 						row[x] ^= t0[x] ^ t1[x] ^ t2[x] ^ t3[x] ^ t4[x] ^ t5[x] ^ t6[x] ^ t7[x];
 				}

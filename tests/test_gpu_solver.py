@@ -191,3 +191,51 @@ def test_synthetic_32768_properties(ctx):
     sysm.eliminate()
     again = sysm.result(0)
     assert np.array_equal(again.origin, got.origin) and again.rank == got.rank
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_synthetic_32768_matches_oracle(ctx, seed):
+    """BASELINE configs[2] bit for bit: rank, pivot columns (the column rank profile) and the
+    particular solution against the oracle's Four-Russians tier (seconds on the host cores)."""
+    n = 32768
+    sysm = ctx.system(n, n)
+    sysm.generate(seed)
+    sysm.eliminate()
+    got = sysm.result(0)
+    A, b, _ = oracle.synth(n, n, seed)
+    want = oracle.solve_packed(A, b, n, 0, tier="m4rm")
+    _assert_same(got, want, 0)
+    assert sysm.check_synthetic(seed, got.origin) == 0
+
+
+def test_forward_paths_agree(ctx):
+    """The one-kernel forward elimination (k_forward) and the per-panel launch chain
+    (GF2B200_FORWARD=launches) are two schedules of the same arithmetic: same echelon
+    form, same answer.  The second context is created with the switch set."""
+    import os
+
+    rnd = random.Random(4242)
+    old = os.environ.get("GF2B200_FORWARD")
+    os.environ["GF2B200_FORWARD"] = "launches"
+    try:
+        ctx2 = _shim.Context(0)
+    finally:
+        if old is None:
+            del os.environ["GF2B200_FORWARD"]
+        else:
+            os.environ["GF2B200_FORWARD"] = old
+    for (m, n, cap) in [(3000, 2500, None), (2500, 3000, None), (5000, 4099, 3000), (1200, 1200, 5)]:
+        A, b = _rand_system(rnd, m, n, rank_cap=cap, consistent=True)
+        g1, g2 = ctx.solve(A, b, n, 1), ctx2.solve(A, b, n, 1)
+        _assert_same(g1, g2, 1)
+    n = 16384
+    outs = []
+    for c in (ctx, ctx2):
+        sysm = c.system(n, n)
+        sysm.generate(5)
+        sysm.eliminate()
+        outs.append((sysm.result(0), sysm.stats()))
+        sysm.close()
+    _assert_same(outs[0][0], outs[1][0], 0)
+    assert outs[0][1]["forward_kernel_launches"] == 1 and outs[1][1]["forward_kernel_launches"] == 0
+    ctx2.close()
