@@ -62,6 +62,10 @@ class CStats(ctypes.Structure):
         ("sweep_bytes_timed", ctypes.c_double),
         ("sweep_launches_timed", ctypes.c_int64),
         ("forward_kernel_launches", ctypes.c_int64),
+        ("ms_basis_solve", ctypes.c_double),
+        ("ms_basis_output", ctypes.c_double),
+        ("basis_sweep_bytes", ctypes.c_double),
+        ("basis_panels", ctypes.c_int64),
     ]
 
     def as_dict(self):

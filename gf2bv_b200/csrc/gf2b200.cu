@@ -18,6 +18,7 @@
  */
 #include "gf2b200_dist.cuh"
 #include "gf2b200_persist.cuh"
+#include "gf2b200_basis.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -184,8 +185,6 @@ static int ctx_init(gf2b200_ctx **out, int device) {
 	c->n_sm = prop.multiProcessorCount;
 	c->stream = c->own_stream;
 	e = cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM);
-	if (e == cudaSuccess)
-		e = cudaFuncSetAttribute(k_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 	/* Tuning switch (off by default, not yet A/B-ed): GF2B200_CARVEOUT=<percent> asks for the
 	 * same shared-memory carve-out in the small per-panel kernels as k_sweep gets (164 of
 	 * 228 KiB = 72), so that the SMs are not re-partitioned three times per panel. */
@@ -368,7 +367,7 @@ static cudaError_t shard_alloc(Shard &s, int world, bool persist) {
 	if (persist && world == 1) {
 		if (e == cudaSuccess) e = cudaMalloc(&s.d_ebuf2, (size_t)M.ns * EBUF_Q * 16);
 		if (e == cudaSuccess) e = cudaMalloc(&s.d_gs, sizeof(GridSync));
-		if (e == cudaSuccess) e = cudaMalloc(&s.d_tpanel, (size_t)(M.nw + 2) * 8);
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_tpanel, ((size_t)(M.nw + 2) + (PERSIST_TRACE ? (size_t)M.nw * 256 * 8 : 0)) * 8);
 	}
 #endif
 	if (world > 1) {
@@ -413,7 +412,7 @@ static int map_peers(gf2b200_system *sys) {
 	cudaIpcMemHandle_t mine;
 	CK(ctx, cudaIpcGetMemHandle(&mine, h.M.base));
 	std::vector<cudaIpcMemHandle_t> all((size_t)G);
-	char *d_h = nullptr;
+	char *d_h = nullptr; /* freed below on every path */
 	CK(ctx, cudaMalloc(&d_h, sizeof(mine) * (size_t)(G + 1)));
 	cudaError_t e = cudaMemcpyAsync(d_h + sizeof(mine) * (size_t)G, &mine, sizeof mine, cudaMemcpyHostToDevice,
 	                                ctx->stream);
@@ -685,7 +684,7 @@ static int forward_single_persist(gf2b200_system *sys, long long *launches) {
 	const Mat &M = h.M;
 	cudaStream_t st = ctx->stream;
 	CK(ctx, cudaMemsetAsync(h.d_gs, 0, sizeof(GridSync), st));
-	CK(ctx, cudaMemsetAsync(h.d_tpanel, 0, (size_t)(M.nw + 2) * 8, st));
+	CK(ctx, cudaMemsetAsync(h.d_tpanel, 0, ((size_t)(M.nw + 2) + (PERSIST_TRACE ? (size_t)M.nw * ctx->n_sm * 8 : 0)) * 8, st));
 	k_extract_pc<<<grid_for(M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(M, 0, h.d_pc[0], 0);
 	cudaLaunchAttribute at[1];
 	at[0].id = cudaLaunchAttributeCooperative;
@@ -716,6 +715,13 @@ static int forward_sharded(gf2b200_system *sys, long long *launches, double *xby
 		k_extract_pc<<<grid_for(h.M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(h.M, 0, h.d_pc[0], 0);
 		(*launches)++;
 	}
+	if (ctx->nccl) {
+		/* Only system_create is collective: a rank may reach this point seconds after its peers
+		 * (load_host, first-launch module load).  A small stream-ordered collective makes every
+		 * rank's stream arrive here before any kernel starts a timed flag wait. */
+		Shard &h0 = sys->sh[0];
+		NK(ctx, g_nccl.AllGather(h0.d_slab, h0.d_slab_all, 8, ncclUint8, ctx->nccl, st));
+	}
 	for (int w = 0; w < nw; w++) {
 		u64 colmask = ~0ULL;
 		if (w == nw - 1 && (sys->n & 63)) colmask = (1ULL << (sys->n & 63)) - 1;
@@ -728,7 +734,7 @@ static int forward_sharded(gf2b200_system *sys, long long *launches, double *xby
 			k_elect<<<1, 32, 0, st>>>(h.xch, G, h.index, w, colmask, h.d_state, h.d_pd, h.d_dp, h.d_pc[w & 1],
 			                          h.d_hist_r, h.d_hist_pm, h.d_hist_owner, epoch, barriers);
 		for (Shard &h : sys->sh)
-			k_apply_pull<<<std::min(nsr, apply_cap), APPLY_THREADS, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_pt, h.d_ebuf, s0a);
+			k_apply_pull<<<std::min(nsr, apply_cap), APPLY_THREADS, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_pt, h.d_ebuf, s0a, h.d_state);
 		if (barriers)
 			for (Shard &h : sys->sh) {
 				k_peer_barrier<<<1, 64, 0, st>>>(h.xch, h.d_pt, h.index, G, epoch, h.d_state);
@@ -736,7 +742,7 @@ static int forward_sharded(gf2b200_system *sys, long long *launches, double *xby
 			}
 		int li = 0;
 		for (Shard &h : sys->sh) {
-			k_apply_commit<<<std::min(nsr, apply_cap), APPLY_THREADS, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_ebuf, s0a);
+			k_apply_commit<<<std::min(nsr, apply_cap), APPLY_THREADS, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_ebuf, s0a, h.d_state);
 			const bool ev = prof && li == 0;
 			if (ev) CK(ctx, cudaEventRecord(sys->ev[6 + 2 * w], st));
 			k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(h.M, h.d_pd, h.d_pc[w & 1],
@@ -853,6 +859,20 @@ extern "C" int gf2b200_system_eliminate(gf2b200_system *sys) {
 #if SW == 8
 	if (persist && hgs.fault)
 		return fail(ctx, GF2B200_ECUDA, "k_forward: a grid-wide wait timed out (the persistent kernel gave up)");
+#if PERSIST_TRACE
+	if (persist)
+		if (const char *tf = getenv("GF2B200_TRACE_FILE")) {
+			const size_t cnt = (size_t)(nw + 2) + (size_t)nw * ctx->n_sm * 8;
+			std::vector<unsigned long long> tr(cnt);
+			cudaMemcpy(tr.data(), sys->sh[0].d_tpanel, cnt * 8, cudaMemcpyDeviceToHost);
+			if (FILE *f = fopen(tf, "wb")) {
+				long long hdr[2] = {nw, ctx->n_sm};
+				fwrite(hdr, 8, 2, f);
+				fwrite(tr.data(), 8, cnt, f);
+				fclose(f);
+			}
+		}
+#endif
 #endif
 	sys->rank = hs[0].r;
 	int bad = 0;
@@ -971,7 +991,7 @@ extern "C" int gf2b200_system_result(gf2b200_system *sys, int mode, gf2b200_resu
 		gf2b200_result_free(out);
 		return fail(ctx, GF2B200_ENOMEM, "malloc");
 	}
-	CK(ctx, cudaMemcpyAsync(out->origin, h.d_x, (size_t)nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	cudaError_t e0 = cudaMemcpyAsync(out->origin, h.d_x, (size_t)nw * 8, cudaMemcpyDeviceToHost, ctx->stream);
 	long long q = 0;
 	for (int w = 0; w < nw; w++) {
 		u64 pm = sys->hist_pm[w];
@@ -980,7 +1000,11 @@ extern "C" int gf2b200_system_result(gf2b200_system *sys, int mode, gf2b200_resu
 			pm &= pm - 1;
 		}
 	}
-	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(ctx->stream);
+	if (e0 != cudaSuccess) {
+		gf2b200_result_free(out); /* callers do not free the result of a failed call */
+		return fail(ctx, GF2B200_ECUDA, "system_result: %s", cudaGetErrorString(e0));
+	}
 	if (mode == 1 && sys->rank < M.n) {
 		/* free columns in M4RI's sigma order: arrangement after "for i<r: swap(i, p_i)"
 		 * (mzd_apply_p_left_trans at _internal.c:348) */
@@ -1023,31 +1047,78 @@ extern "C" int gf2b200_system_result(gf2b200_system *sys, int mode, gf2b200_resu
 			out->status = GF2B200_OK;
 			return GF2B200_OK;
 		}
-		size_t xs_bytes = (size_t)M.ns * SBYTES;
-		if (xs_bytes > 200 * 1024) {
-			gf2b200_result_free(out);
-			return fail(ctx, GF2B200_EINVAL, "n too large for the kernel-basis back-substitution kernel");
-		}
+		/* blocked multi-right-hand-side triangular solve on the free-column matrix
+		 * (gf2b200_basis.cuh): F = U2, then per panel, last first, the Four-Russians sweep */
+		Mat F;
+		memset(&F, 0, sizeof F);
+		F.m = r;
+		F.n = d;
+		F.nw = (int)((d + 63) / 64);
+		F.ns = (F.nw + SW - 1) / SW;
+		F.mp = (std::max<long long>(r, 1) + 15) / 16 * 16;
 		long long *d_free = nullptr;
-		u64 *d_basis = nullptr;
+		u64 *d_basis = nullptr, *d_pcF = nullptr;
+		uint4 *d_ebufF = nullptr;
+		PanelDesc *d_pdF = nullptr;
 		/* batches bound the device buffer for huge nullities */
 		const long long batch = std::min<long long>(d, std::max<long long>(1, (1LL << 28) / ((long long)nw * 8)));
 		cudaError_t e = cudaMalloc(&d_free, (size_t)d * 8);
 		if (e == cudaSuccess) e = cudaMalloc(&d_basis, (size_t)batch * nw * 8);
+		if (e == cudaSuccess) e = cudaMalloc(&F.base, (size_t)F.ns * (size_t)F.mp * SBYTES);
+		if (e == cudaSuccess) e = cudaMalloc(&d_pcF, (size_t)F.mp * 8);
+		if (e == cudaSuccess) e = cudaMalloc(&d_ebufF, (size_t)F.ns * EBUF_Q * 16);
+		if (e == cudaSuccess) e = cudaMalloc(&d_pdF, sizeof(PanelDesc));
 		if (e == cudaSuccess)
 			e = cudaMemcpyAsync(d_free, sigma.data() + r, (size_t)d * 8, cudaMemcpyHostToDevice, ctx->stream);
+		cudaEvent_t tb0 = sys->ev[3], tb1 = sys->ev[4], tb2 = sys->ev[5];
+		double bk_bytes = 0;
+		long long bk_panels = 0;
+		if (e == cudaSuccess) e = cudaEventRecord(tb0, ctx->stream);
+		if (e == cudaSuccess && r > 0) {
+			k_basis_gather<<<grid_for(r * F.ns * SW, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(M, F, d_free, h.d_hist_r, r, d);
+			for (int w = nw - 1; w >= 0 && e == cudaSuccess; --w) {
+				const u64 pm = sys->hist_pm[w];
+				const long long r_w = h.hist_r[w];
+				if (!pm || r_w <= 0) continue;
+				k_basis_prep<<<grid_for(std::max<long long>(r_w, (long long)F.ns * EBUF_Q), 256, ctx->n_sm * 8), 256, 0,
+				               ctx->stream>>>(M, F, w, pm, r_w, d_pcF, d_ebufF, d_pdF);
+				Mat Fv = F;
+				Fv.m = r_w; /* the rows above the panel */
+				k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, ctx->stream>>>(Fv, d_pdF, d_pcF, nullptr, d_ebufF, 0, 0,
+				                                                              nullptr, nullptr, nullptr, nullptr, 0);
+				bk_bytes += 2.0 * (double)r_w * (double)SBYTES * (double)F.ns;
+				bk_panels++;
+			}
+			e = cudaGetLastError();
+		}
+		if (e == cudaSuccess) e = cudaEventRecord(tb1, ctx->stream);
 		for (long long b0 = 0; e == cudaSuccess && b0 < d; b0 += batch) {
 			long long nb = std::min(batch, d - b0);
-			k_backsub<<<(unsigned)nb, 1024, xs_bytes, ctx->stream>>>(M, h.d_hist_r, h.d_hist_pm, d_free + b0, 0,
-			                                                        d_basis);
+			k_basis_scatter<<<grid_for(nb * nw, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
+			    F, h.d_hist_r, h.d_hist_pm, d_free, nw, b0, nb, d_basis);
 			e = cudaGetLastError();
 			if (e == cudaSuccess)
 				e = cudaMemcpyAsync(out->basis + b0 * nw, d_basis, (size_t)nb * nw * 8,
 				                    cudaMemcpyDeviceToHost, ctx->stream);
 			if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
 		}
+		if (e == cudaSuccess) e = cudaEventRecord(tb2, ctx->stream);
+		if (e == cudaSuccess) e = cudaEventSynchronize(tb2);
+		if (e == cudaSuccess) {
+			float ms1 = 0, ms2 = 0;
+			cudaEventElapsedTime(&ms1, tb0, tb1);
+			cudaEventElapsedTime(&ms2, tb1, tb2);
+			sys->stats.ms_basis_solve = ms1;
+			sys->stats.ms_basis_output = ms2;
+			sys->stats.basis_sweep_bytes = bk_bytes;
+			sys->stats.basis_panels = bk_panels;
+		}
 		cudaFree(d_free);
 		cudaFree(d_basis);
+		cudaFree(F.base);
+		cudaFree(d_pcF);
+		cudaFree(d_ebufF);
+		cudaFree(d_pdF);
 		if (e != cudaSuccess) {
 			gf2b200_result_free(out);
 			return fail(ctx, GF2B200_ECUDA, "kernel basis: %s", cudaGetErrorString(e));

@@ -88,11 +88,16 @@ __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) { __atom
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ unsigned long long globaltimer_ns() { return (unsigned long long)(emu_now_ms() * 1e6); }
 #endif
-/* spin until *flag >= epoch (epochs only grow); gives up after ~4 s and reports a fault */
+/* spin until *flag >= epoch (epochs only grow); gives up after DIST_TIMEOUT_NS and reports a
+ * fault.  The ranks' streams meet in a small collective before the first wait of an
+ * elimination (forward_sharded), so the time-out only has to cover one panel's skew. */
+#ifndef DIST_TIMEOUT_NS
+#define DIST_TIMEOUT_NS 30000000000ULL
+#endif
 __device__ __forceinline__ bool wait_flag(const unsigned *flag, unsigned epoch) {
 	const unsigned long long t0 = globaltimer_ns();
 	while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
-		if (globaltimer_ns() - t0 > 4000000000ULL) return false;
+		if (globaltimer_ns() - t0 > DIST_TIMEOUT_NS) return false;
 		__nanosleep(64);
 	}
 	return true;
@@ -109,6 +114,7 @@ k_select_publish(Mat M, const u64 *__restrict__ pc, u64 colmask, const SolverSta
 	__shared__ SelectSmem S;
 	__shared__ u64 blk[CAND_W];
 	const int tid = threadIdx.x;
+	if (*(const volatile int *)&st->fault) return; /* an earlier wait timed out: the elimination is void */
 	select_init(S);
 	__syncthreads();
 	select_scan(S, pc, st->r_loc, M.m, colmask);
@@ -144,6 +150,7 @@ k_elect(const XchBlock *__restrict__ xch, int G, int me, int w, u64 colmask, Sol
 	__shared__ int sel[64];
 	__shared__ int topsel[64], mv_src[64], mv_dst[64];
 	const int lane = threadIdx.x;
+	if (*(volatile int *)&st->fault) return;
 	if (barriers) {
 		bool ok = true;
 		for (int g = lane; g < G; g += 32) ok = ok && wait_flag(&xch->flagA[g], epoch);
@@ -263,9 +270,10 @@ k_elect(const XchBlock *__restrict__ xch, int G, int me, int w, u64 colmask, Sol
  * ---------------------------------------------------------------------- */
 __global__ void __launch_bounds__(APPLY_THREADS)
 k_apply_pull(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restrict__ dp,
-             const PeerTable *__restrict__ pt, uint4 *__restrict__ ebuf, int s0) {
+             const PeerTable *__restrict__ pt, uint4 *__restrict__ ebuf, int s0, const SolverState *st) {
 	__shared__ uint4 Sel[64][SQ];
 	__shared__ u64 sTB[64];
+	if (*(const volatile int *)&st->fault) return;
 	const int k = pd->k;
 	if (k == 0) return;
 	const int tid = threadIdx.x, rr = tid / SQ, ch = tid % SQ;
@@ -300,6 +308,7 @@ __global__ void __launch_bounds__(64)
 k_peer_barrier(XchBlock *xch, const PeerTable *__restrict__ pt, int me, int G, unsigned epoch,
                SolverState *st) {
 	const int g = threadIdx.x;
+	if (*(volatile int *)&st->fault) return;
 	__threadfence_system();
 	bool ok = true;
 	if (g < G) {
@@ -313,9 +322,10 @@ k_peer_barrier(XchBlock *xch, const PeerTable *__restrict__ pt, int me, int G, u
  * r + (index among its own); displaced rows go to the vacated positions */
 __global__ void __launch_bounds__(APPLY_THREADS)
 k_apply_commit(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restrict__ dp,
-               const uint4 *__restrict__ ebuf, int s0) {
+               const uint4 *__restrict__ ebuf, int s0, const SolverState *st) {
 	__shared__ uint4 Dis[64][SQ];
 	__shared__ int ssrc[64], sdst[64], smyidx[64];
+	if (*(const volatile int *)&st->fault) return;
 	const int k = pd->k;
 	if (k == 0) return;
 	const int tid = threadIdx.x, rr = tid / SQ, ch = tid % SQ;

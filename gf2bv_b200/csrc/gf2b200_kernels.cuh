@@ -757,9 +757,11 @@ sweep_body(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_c
 	const long long m = M.m;
 	if (r1 >= m) return;
 	const int wn = w + 1; /* next panel word (or the b word): always exists */
-	const int snext = wn >> SW_SHIFT;
+	/* pc_next == nullptr: a sweep that feeds no later panel (the kernel-basis solve): no strip is "next" */
+	const int snext = pc_next ? (wn >> SW_SHIFT) : -1;
 	if (k == 0) {
 		/* nothing to eliminate: only hand the next word column to k_select */
+		if (!pc_next) return;
 		for (long long i = r1 + blockIdx.x * (long long)SWEEP_THREADS + tid; i < m;
 		     i += (long long)gridDim.x * SWEEP_THREADS)
 			pc_next[i] = M.base[widx(M, i, wn)];
@@ -976,66 +978,6 @@ __global__ void k_check(Mat M, SolverState *st) {
 	     i += (long long)gridDim.x * blockDim.x)
 		bad |= (int)(M.base[widx(M, i, M.nw)] & 1);
 	if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&st->inconsistent, 1);
-}
-
-/* ------------------------------------------------------------------------
- * k_backsub: back-substitution over the echelon rows, last panel first.
- * One CTA per right-hand side; x (extended with x[nw] = use_b so the b word is
- * just another column) lives in shared memory.  rhs 0 with use_b = 1 is the
- * particular solution (free variables 0, _internal.c:440-454); with freecols !=
- * nullptr CTA i computes the kernel vector that is 1 at free column freecols[i]
- * and 0 at the other free columns (_internal.c:330-348: U1^-1 U2 ; I).
- * ---------------------------------------------------------------------- */
-__global__ void __launch_bounds__(1024, 1)
-k_backsub(Mat M, const long long *__restrict__ hist_r, const u64 *__restrict__ hist_pm,
-          const long long *__restrict__ freecols, int use_b, u64 *__restrict__ xout) {
-	extern __shared__ __align__(128) u64 xs[];
-	__shared__ unsigned long long newbits;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int WT = M.ns * SW;
-	for (int w = tid; w < WT; w += blockDim.x) xs[w] = 0;
-	__syncthreads();
-	if (tid == 0) {
-		if (use_b) xs[M.nw] = 1;
-		if (freecols) {
-			long long f = freecols[blockIdx.x];
-			xs[f >> 6] |= 1ULL << (f & 63);
-		}
-		newbits = 0;
-	}
-	__syncthreads();
-	const int wl = lane & (SW - 1), so = lane >> SW_SHIFT;
-	for (int p = M.nw - 1; p >= 0; --p) {
-		const u64 pm = hist_pm[p];
-		if (!pm) continue;
-		const int k = __popcll(pm);
-		const long long r = hist_r[p];
-		for (int j = warp; j < k; j += 32) {
-			const u64 *rowp = M.base + (r + j) * SW + wl;
-			u64 acc = 0;
-			int s = (p >> SW_SHIFT) + so;
-#pragma unroll 4
-			for (; s < M.ns; s += 32 / SW) {
-				int wd = s * SW + wl;
-				u64 a = rowp[(long long)s * M.mp * SW];
-				if (wd >= p) acc ^= a & xs[wd];
-			}
-			int par = __popcll(acc) & 1;
-			par = __reduce_xor_sync(0xffffffffu, par);
-			if (lane == 0 && par) {
-				u64 t = pm;
-				for (int q = 0; q < j; q++) t &= t - 1;
-				atomicOr(&newbits, t & (~t + 1));
-			}
-		}
-		__syncthreads();
-		if (tid == 0) {
-			xs[p] |= newbits;
-			newbits = 0;
-		}
-		__syncthreads();
-	}
-	for (int w = tid; w < M.nw; w += blockDim.x) xout[(long long)blockIdx.x * M.nw + w] = xs[w];
 }
 
 } /* namespace gf2b200 */

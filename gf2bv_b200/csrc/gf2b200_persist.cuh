@@ -47,7 +47,14 @@ struct GridSync {
 	int fault;           /* a wait timed out */
 	int done_w;          /* panels finished (diagnostic) */
 	unsigned pad[2];
+	/* what every CTA needs at the top of a panel, in ONE 16-byte load: {valid = panel + 1,
+	 * r1 = first active row, pm lo, pm hi}; slot = panel & 1 (k = popcount(pm)) */
+	uint4 hdr[2];
 };
+
+__device__ __forceinline__ void hdr_publish(GridSync *gs, int w, long long r1, u64 pm) {
+	__stcg(&gs->hdr[w & 1], make_uint4((unsigned)(w + 1), (unsigned)r1, (unsigned)pm, (unsigned)(pm >> 32)));
+}
 
 /* How the sweep reads a row's coefficient (the panel word pc_cur[row]):
  *   0  ld.cg (L2 only)
@@ -60,8 +67,26 @@ struct GridSync {
 #ifndef PERSIST_CF_LOAD
 #define PERSIST_CF_LOAD 1
 #endif
+/* PERSIST_FIRST_TILE_LDG 1: the FIRST E tile of a panel (needed right after the grid barrier,
+ * by all 148 CTAs at once) is read with 256 plain 16-byte ld.cg instead of the proxy fence +
+ * bulk copy + mbarrier wait; later tiles keep the prefetching bulk copy. */
+#ifndef PERSIST_FIRST_TILE_LDG
+#define PERSIST_FIRST_TILE_LDG 0
+#endif
 #ifndef PERSIST_UNCOND_LOADS
-#define PERSIST_UNCOND_LOADS 0
+#define PERSIST_UNCOND_LOADS 1
+#endif
+/* Developer trace (-DPERSIST_TRACE=1, scripts/trace_forward.py): thread 32 of every CTA (NOT a
+ * lane of warp 0: a lone lane stamping there leaves warp 0 divergent and sends the search's
+ * warp collectives down their slow BRA.DIV paths -- a 16 us search read 70 us) stamps
+ * globaltimer at 8 points of every panel into t_panel + (nw + 2) + (w * gridDim + cta) * 8. */
+#ifndef PERSIST_TRACE
+#define PERSIST_TRACE 0
+#endif
+#if PERSIST_TRACE
+#define TRACE(slot) do { if (tid == 32) t_panel[(size_t)(nw + 2) + ((size_t)w * G + blockIdx.x) * 8 + (slot)] = gtimer_ns(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
 #endif
 #ifndef PERSIST_TIMEOUT_NS
 #define PERSIST_TIMEOUT_NS 20000000000ULL
@@ -120,21 +145,51 @@ __device__ __forceinline__ bool persist_wait(const unsigned *p, unsigned target,
 __device__ __forceinline__ bool grid_barrier(GridSync *gs, int *s_ok) {
 	__syncthreads();
 	if (threadIdx.x == 0) {
-		__threadfence();
-		const unsigned g = ld_acquire_gpu(&gs->gen);
+		const unsigned g = *(volatile unsigned *)&gs->gen; /* cannot advance before this CTA arrives */
+		__threadfence();                                   /* this CTA's writes before its arrival */
 		bool ok = true;
 		if (atomicAdd(&gs->count, 1u) == gridDim.x - 1) {
 			atomicExch(&gs->count, 0u);
-			__threadfence();
-			st_release_gpu(&gs->gen, g + 1);
+			st_release_gpu(&gs->gen, g + 1); /* cumulative: orders everything this thread observed */
 		} else {
-			ok = persist_wait(&gs->gen, g + 1, nullptr, gs);
+			ok = persist_wait(&gs->gen, g + 1, nullptr, gs); /* acquire loads */
 		}
-		__threadfence();
 		*s_ok = (ok && !*(volatile int *)&gs->fault) ? 1 : 0;
 	}
 	__syncthreads();
 	return *s_ok != 0;
+}
+
+/* Look-ahead pivot search, warp 0 only: the 1024 panel words of the first active rows sit in
+ * S.qv (slot = row - base8, 0 for rows outside the active range) where the sweep of unit 0
+ * left them -- no reload from global memory, no compaction pass.  32 slots at a time; zero
+ * words are skipped by ballot; stops as soon as every column of the panel is a pivot. */
+__device__ __forceinline__ void window_search(SelectSmem &S, long long base8, u64 colmask, int lane) {
+	for (int c = lane; c < 64; c += 32) {
+		S.sel[c] = -1;
+		S.topsel[c] = 0;
+	}
+	__syncwarp();
+	WarpBasis W;
+	W.B0 = W.B1 = W.T0 = W.T1 = 0;
+	W.pm = 0;
+	W.nsel = 0;
+	for (int g = 0; g < SWEEP_RU / 32 && W.pm != colmask; g++) {
+		const u64 mine = S.qv[32 * g + lane] & colmask;
+		unsigned bal = __ballot_sync(0xffffffffu, mine != 0);
+		while (bal && W.pm != colmask) {
+			const int src = __ffs((int)bal) - 1;
+			bal &= bal - 1;
+			wb_insert(W, S.sel, shfl64(mine, src), 0, (int)(base8 + 32 * g + src), lane);
+		}
+	}
+	wb_store(W, S.B, S.TB, lane);
+	__syncwarp();
+	if (lane == 0) {
+		S.pm = W.pm;
+		S.nsel = W.nsel;
+	}
+	__syncwarp();
 }
 
 /* Shared-memory image of the panel description an apply needs. */
@@ -230,11 +285,6 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 	}
 	__syncthreads();
 	unsigned phase = 0;
-	const int ch = tid % SQ, rl = tid / SQ;
-	const int h = rl & 1;
-	const unsigned char *Tbe = reinterpret_cast<const unsigned char *>(TD + 4 * h + ch);
-	const unsigned char *Tbo = reinterpret_cast<const unsigned char *>(TD + 4 * (1 - h) + ch);
-	const unsigned bsel = h ? 0x2301u : 0x3210u;
 
 	for (int w = w_begin; w < w_end; ++w) {
 		u64 *pc_cur = (w & 1) ? pc1 : pc0, *pc_next = (w & 1) ? pc0 : pc1;
@@ -242,9 +292,11 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 		uint4 *ebuf_next = (w & 1) ? ebuf0 : ebuf1;
 		PanelDesc *pd = pd2 + (w & 1), *pdn = pd2 + ((w + 1) & 1);
 		if (blockIdx.x == 0 && tid == 0) t_panel[w] = gtimer_ns();
+		TRACE(0);
 
 		/* ---- slow path: nobody settled this panel ahead of time ---------------- */
-		if (*(volatile int *)&pd->valid != w + 1) {
+		uint4 hd = __ldcg(&gs->hdr[w & 1]);
+		if ((int)hd.x != w + 1) {
 			u64 colmask = ~0ULL;
 			if (w == nw - 1 && (M.n & 63)) colmask = (1ULL << (M.n & 63)) - 1;
 			if (blockIdx.x == 0) {
@@ -252,7 +304,11 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 				select_init(S);
 				__syncthreads();
 				select_scan(S, pc_cur, r, m, colmask);
-				if (tid < 32) select_finalize(S, pc_cur, w, r, st, pd, hist_r, hist_pm);
+				if (tid < 32) {
+					select_finalize(S, pc_cur, w, r, st, pd, hist_r, hist_pm);
+					__syncwarp();
+					if (tid == 0) hdr_publish(gs, w, r + S.nsel, S.pm);
+				}
 			}
 			if (!grid_barrier(gs, s_ok)) return;
 			const int s0a = w >> SW_SHIFT;
@@ -260,11 +316,12 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 			persist_apply(M, pd, const_cast<uint4 *>(ebuf), AP, mine > 0 ? mine : 0,
 			              [&](int i) { return s0a + (int)blockIdx.x + i * G; });
 			if (!grid_barrier(gs, s_ok)) return;
+			hd = __ldcg(&gs->hdr[w & 1]);
 		}
 
-		const int k = *(volatile int *)&pd->k;
-		const long long r1 = *(volatile long long *)&pd->r1;
-		const u64 pm = *(volatile u64 *)&pd->pm;
+		const long long r1 = (long long)hd.y;
+		const u64 pm = ((u64)hd.w << 32) | hd.z;
+		const int k = __popcll(pm);
 		const int wn = w + 1;
 		const bool has_next = wn < nw;
 		if (r1 >= m) {
@@ -297,24 +354,44 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 		u64 colmask_next = ~0ULL;
 		if (wn == nw - 1 && (M.n & 63)) colmask_next = (1ULL << (M.n & 63)) - 1;
 		if (u0 < u1) {
+			/* per-thread lookup constants are (re)derived here, not kept live across the search /
+			 * apply / barrier code of the panel loop (64 registers per thread, no spills) */
+			const int ch = tid % SQ, rl = tid / SQ;
+			const int h = rl & 1;
+			const unsigned char *Tbe = reinterpret_cast<const unsigned char *>(TD + 4 * h + ch);
+			const unsigned char *Tbo = reinterpret_cast<const unsigned char *>(TD + 4 * (1 - h) + ch);
+			const unsigned bsel = h ? 0x2301u : 0x3210u;
 			int cur = -1, fetched = -1;
 			const int s_last = s0 + (int)((u1 - 1) / nchunks);
-			for (long long u = u0; u < u1; ++u) {
-				const int s = s0 + (int)(u / nchunks);
-				const long long chunk = u % nchunks;
+			int s = s0 + (int)(u0 / nchunks);
+			long long chunk = u0 % nchunks; /* (strip, row chunk) of unit u, advanced without dividing */
+			for (long long u = u0; u < u1; ++u, ++chunk) {
+				if (chunk == nchunks) {
+					chunk = 0;
+					++s;
+				}
 				if (s != cur) {
 					__syncthreads(); /* everyone is done with the previous tables */
-					if (fetched != s && tid == 0) {
-						fence_proxy_async();
-						mbar_expect_tx(bar, EBUF_Q * 16);
-						tma_bulk_g2s(E, ebuf + (long long)s * EBUF_Q, EBUF_Q * 16, bar);
+#if PERSIST_FIRST_TILE_LDG
+					if (cur < 0) {
+						if (tid < EBUF_Q) E[tid] = __ldcg(ebuf + (long long)s * EBUF_Q + tid);
+						__syncthreads();
+					} else
+#endif
+					{
+						if (fetched != s && tid == 0) {
+							fence_proxy_async();
+							mbar_expect_tx(bar, EBUF_Q * 16);
+							tma_bulk_g2s(E, ebuf + (long long)s * EBUF_Q, EBUF_Q * 16, bar);
+						}
+						mbar_wait(bar, phase);
+						phase ^= 1;
 					}
-					mbar_wait(bar, phase);
-					phase ^= 1;
 					const bool more = SWEEP_EARLY_TILE && (s < s_last) && !(has_next && u == 0);
 					if (more && tid == 0) fence_proxy_async();
 					sweep_build_tables(TD, P, E, tid, more ? ebuf + (long long)(s + 1) * EBUF_Q : nullptr, bar);
 					fetched = more ? s + 1 : -1;
+					if (cur < 0) TRACE(1); /* first tables of the panel built */
 					cur = s;
 				}
 				const long long row0 = base8 + chunk * SWEEP_RU + rl;
@@ -345,7 +422,10 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 				}
 #pragma unroll
 				for (int q = 0; q < SWEEP_U; q++) {
-					if (!act[q]) continue;
+					if (!act[q]) {
+						if (has_next && u == 0 && ch == nch) S.qv[rl + (SWEEP_THREADS / SQ) * q] = 0;
+						continue;
+					}
 					uint4 v = d[q];
 					const unsigned lo = __byte_perm((unsigned)cf[q], 0, bsel);
 					const unsigned hi = __byte_perm((unsigned)(cf[q] >> 32), 0, bsel);
@@ -362,33 +442,37 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 					__stcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ, v);
 					if (force && ch == nch) {
 						const long long row = row0 + (SWEEP_THREADS / SQ) * q;
-						__stcg(pc_next + row, (wn & 1) ? (((u64)v.w << 32) | v.z) : (((u64)v.y << 32) | v.x));
+						const u64 nv = (wn & 1) ? (((u64)v.w << 32) | v.z) : (((u64)v.y << 32) | v.x);
+						__stcg(pc_next + row, nv);
+						if (has_next && u == 0) S.qv[rl + (SWEEP_THREADS / SQ) * q] = nv; /* for the look-ahead search */
 					}
 				}
 				if (has_next && u == 0) {
 					/* look-ahead: this CTA just produced word w+1 of the first active rows; search
 					 * them for the next panel's pivots while the other SMs keep streaming */
 					__threadfence_block();
-					__syncthreads();
-					select_init(S);
-					__syncthreads();
-					const long long lim = min(m, base8 + (long long)SWEEP_RU);
-					select_scan(S, pc_next, r1, lim, colmask_next);
+					__syncthreads(); /* S.qv complete; this unit's pc_next words are written */
+					TRACE(6);
 					if (tid < 32) {
+						const long long lim = min(m, base8 + (long long)SWEEP_RU);
+						window_search(S, base8, colmask_next, tid);
 						const bool final_ = (S.pm == colmask_next || lim == m);
 						if (final_) select_finalize(S, pc_next, wn, r1, st, pdn, hist_r, hist_pm);
 						__syncwarp();
 						if (tid == 0) {
+							if (final_) hdr_publish(gs, wn, r1 + S.nsel, S.pm);
 							__threadfence();
 							st_release_gpu(final_ ? &gs->sel_flag : &gs->need_full, (unsigned)wn + 1);
 						}
 					}
 					__syncthreads();
+					TRACE(7);
 				}
 			}
 		}
 
 		/* ---- apply(w+1) for the strips whose first-rows unit this CTA swept ------- */
+		TRACE(2); /* my units are done */
 		if (has_next) {
 			__syncthreads(); /* the tables are dead: their space is the apply scratch */
 			if (tid == 0) {
@@ -401,6 +485,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 			__syncthreads();
 			const int state = *s_state;
 			if (state == 0) return;
+			TRACE(3); /* the next panel's description is there */
 			if (state == 1 && u0 < u1) {
 				const long long sa = (u0 + nchunks - 1) / nchunks, sb = (u1 - 1) / nchunks; /* strips (relative) whose chunk 0 is mine */
 				const int cnt = (int)(sb - sa + 1);
@@ -408,7 +493,9 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 			}
 		}
 		if (blockIdx.x == 0 && tid == 0) gs->done_w = wn;
+		TRACE(4); /* apply done */
 		if (!grid_barrier(gs, s_ok)) return;
+		TRACE(5);
 	}
 	if (blockIdx.x == 0 && tid == 0) t_panel[w_end] = gtimer_ns();
 }

@@ -76,6 +76,12 @@ typedef struct {
 	                                  * ms_sweep is then that kernel's duration (always measured),
 	                                  * sweep_launches counts its panels with work and ms_sweep_max /
 	                                  * sweep_bytes_max describe its longest panel.  0: per-panel launches */
+	/* last gf2b200_system_result(mode 1) on a one-GPU system: the blocked multi-right-hand-side
+	 * triangular solve of the kernel basis (replaces mzd_trsm_upper_left, _internal.c:343) */
+	double ms_basis_solve;    /* gather of the free columns + every backward sweep */
+	double ms_basis_output;   /* scatter into basis vectors + D2H */
+	double basis_sweep_bytes; /* algorithmic bytes of the backward sweeps: sum 2 * rows above * row bytes of F */
+	int64_t basis_panels;
 } gf2b200_stats;
 
 int gf2b200_abi_version(void);

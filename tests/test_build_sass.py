@@ -52,7 +52,15 @@ def test_resource_usage(lib):
     assert len(sweep) == 1
     regs = int(re.search(r"REG:(\d+)", sweep[0]).group(1))
     assert regs <= 64, "k_sweep must fit 1024 threads x 64 registers on one SM"
+    fwd = [v for k, v in usage.items() if "k_forward" in k]
+    assert len(fwd) == 1 and int(re.search(r"REG:(\d+)", fwd[0]).group(1)) <= 64
     for name, body in usage.items():
+        if "k_forward" in name:
+            # the persistent kernel parks three panel-loop induction values on the stack (one
+            # store/load per PANEL); its streaming loop must stay free of local-memory traffic --
+            # checked on the SASS in test_forward_sass_shape
+            assert int(re.search(r"STACK:(\d+)", body).group(1)) <= 32 and "LOCAL:0" in body, body
+            continue
         assert "STACK:0" in body and "LOCAL:0" in body, f"{name} spills to local memory: {body.strip()}"
 
 
@@ -66,3 +74,24 @@ def test_sweep_sass_shape(lib):
     assert "REDUX.XOR" in sweep, "fused pivot search folds candidates with warp-wide REDUX"
     # 4 row pieces x 8 lookups in the streaming loop + the table build
     assert sweep.count("LDS.128") >= 32
+
+
+def test_forward_sass_shape(lib):
+    """k_forward (the persistent one-kernel forward elimination): same streaming loop as k_sweep
+    -- four 128-bit row pieces in flight, eight 128-bit lookups each, no local-memory access
+    between the first row load and the last row store -- plus the TMA tile copy, the release /
+    acquire flags of the look-ahead and the grid barrier."""
+    txt = subprocess.run([CUOBJDUMP, "-sass", str(lib)], capture_output=True, text=True).stdout
+    fn = _functions(txt, r"Function : (\S+)")
+    fwd = next(v for k, v in fn.items() if "k_forward" in k).splitlines()
+    loads = [i for i, l in enumerate(fwd) if "LDG.E.128" in l and "@P" in l]
+    assert len(loads) >= 4
+    first = loads[0]
+    stores = [i for i, l in enumerate(fwd) if "STG.E.128" in l and i > first]
+    last = stores[3]
+    hot = "\n".join(fwd[first:last + 1])
+    assert hot.count("LDS.128") == 32 and "LDL" not in hot and "STL" not in hot
+    body = "\n".join(fwd)
+    assert "UBLKCP" in body and "SYNCS.PHASECHK" in body
+    assert "REDUX.XOR" in body, "look-ahead pivot search"
+    assert "CCTL.IVALL" in body, "acquire loads invalidate L1: cached coefficient loads after a barrier are safe"
