@@ -74,6 +74,7 @@ struct Shard {
 	uint4 *d_ebuf2;
 	void *d_gs;
 	unsigned long long *d_tpanel;
+	u64 *d_cand; /* two candidate lists of PERSIST_CAND_MAX {row, word} pairs (k_forward's slow path) */
 	/* sharded systems only */
 	DistPanel *d_dp;
 	unsigned char *d_hist_owner;
@@ -330,6 +331,7 @@ static void shard_free(Shard &s) {
 	cudaFree(s.d_ebuf2);
 	cudaFree(s.d_gs);
 	cudaFree(s.d_tpanel);
+	cudaFree(s.d_cand);
 	for (void *p : s.ipc_opened) cudaIpcCloseMemHandle(p);
 	s.ipc_opened.clear();
 	cudaFree(s.d_dp);
@@ -367,6 +369,7 @@ static cudaError_t shard_alloc(Shard &s, int world, bool persist) {
 	if (persist && world == 1) {
 		if (e == cudaSuccess) e = cudaMalloc(&s.d_ebuf2, (size_t)M.ns * EBUF_Q * 16);
 		if (e == cudaSuccess) e = cudaMalloc(&s.d_gs, sizeof(GridSync));
+		if (e == cudaSuccess) e = cudaMalloc(&s.d_cand, (size_t)2 * PERSIST_CAND_MAX * 2 * 8);
 		if (e == cudaSuccess) e = cudaMalloc(&s.d_tpanel, ((size_t)(M.nw + 2) + (PERSIST_TRACE ? (size_t)M.nw * 256 * 8 : 0)) * 8);
 	}
 #endif
@@ -474,7 +477,7 @@ extern "C" int gf2b200_system_create(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2
 		h.d_pc[0] = h.d_pc[1] = nullptr;
 		h.d_state = nullptr; h.d_pd = nullptr; h.d_hist_r = nullptr; h.d_hist_pm = nullptr;
 		h.d_ebuf = nullptr; h.d_dp = nullptr; h.d_hist_owner = nullptr;
-		h.d_ebuf2 = nullptr; h.d_gs = nullptr; h.d_tpanel = nullptr;
+		h.d_ebuf2 = nullptr; h.d_gs = nullptr; h.d_tpanel = nullptr; h.d_cand = nullptr;
 		h.xch = nullptr; h.d_pt = nullptr;
 		h.d_x = h.d_slab = h.d_slab_all = nullptr;
 		e = shard_alloc(h, ctx->world, ctx->persist != 0);
@@ -692,7 +695,7 @@ static int forward_single_persist(gf2b200_system *sys, long long *launches) {
 	cudaLaunchConfig_t cfg = {dim3(ctx->n_sm), dim3(SWEEP_THREADS), PERSIST_SMEM, st, at, 1};
 	CK(ctx, cudaEventRecord(sys->ev[3], st));
 	CK(ctx, cudaLaunchKernelEx(&cfg, k_forward, M, h.d_pc[0], h.d_pc[1], h.d_ebuf, h.d_ebuf2, h.d_pd, h.d_state,
-	                           h.d_hist_r, h.d_hist_pm, (GridSync *)h.d_gs, h.d_tpanel, 0, M.nw));
+	                           h.d_hist_r, h.d_hist_pm, (GridSync *)h.d_gs, h.d_tpanel, h.d_cand, 0, M.nw));
 	CK(ctx, cudaEventRecord(sys->ev[4], st));
 	k_check<<<grid_for(M.m, 256, ctx->n_sm * 8), 256, 0, st>>>(M, h.d_state);
 	*launches += 3;

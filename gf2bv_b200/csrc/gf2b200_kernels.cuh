@@ -284,15 +284,24 @@ struct SelectSmem {
 	int nsel;
 };
 
+/* list != nullptr: scan a compacted candidate list instead of the dense column -- entry i in
+ * [r, m) is the pair {row, panel word} at list[2i], list[2i+1] (k_forward's slow path) */
 __device__ __forceinline__ void select_scan(SelectSmem &S, const u64 *__restrict__ pc, long long r,
-                                            long long m, u64 colmask) {
+                                            long long m, u64 colmask, const u64 *list = nullptr) {
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	for (long long base = r; base < m; base += SEL_THREADS) {
 		u64 pm = S.pm;
 		if (pm == colmask) break;
 		long long i = base + tid;
 		/* ld.cg: inside the persistent kernel another SM wrote these words moments ago */
-		u64 v = (i < m) ? (__ldcg(pc + i) & colmask) : 0;
+		u64 v;
+		int row = (int)i;
+		if (list) {
+			v = (i < m) ? (__ldcg(list + 2 * i + 1) & colmask) : 0;
+			if (i < m) row = (int)__ldcg(list + 2 * i);
+		} else {
+			v = (i < m) ? (__ldcg(pc + i) & colmask) : 0;
+		}
 		u64 tv = 0;
 		u64 x = v & pm;
 		while (x) {
@@ -315,7 +324,7 @@ __device__ __forceinline__ void select_scan(SelectSmem &S, const u64 *__restrict
 			int pos = off + __popc(bal & ((1u << lane) - 1));
 			S.qv[pos] = v;
 			S.qtv[pos] = tv;
-			S.qrow[pos] = (int)i;
+			S.qrow[pos] = row;
 		}
 		__syncthreads();
 		if (warp == 0) {

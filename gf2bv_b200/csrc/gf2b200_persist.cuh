@@ -46,7 +46,7 @@ struct GridSync {
 	unsigned need_full;  /* panel index + 1 for which the first 1024 rows were not enough */
 	int fault;           /* a wait timed out */
 	int done_w;          /* panels finished (diagnostic) */
-	unsigned pad[2];
+	unsigned cand_cnt[2]; /* candidate rows collected for panel (slot = panel & 1): see PERSIST_CAND_MAX */
 	/* what every CTA needs at the top of a panel, in ONE 16-byte load: {valid = panel + 1,
 	 * r1 = first active row, pm lo, pm hi}; slot = panel & 1 (k = popcount(pm)) */
 	uint4 hdr[2];
@@ -85,8 +85,20 @@ __device__ __forceinline__ void hdr_publish(GridSync *gs, int w, long long r1, u
 #endif
 #if PERSIST_TRACE
 #define TRACE(slot) do { if (tid == 32) t_panel[(size_t)(nw + 2) + ((size_t)w * G + blockIdx.x) * 8 + (slot)] = gtimer_ns(); } while (0)
+/* inside warp 0: all 32 lanes store (warp-uniform, no divergence); slots 8.. of CTA 0 live in the trace row of CTA 1 + */
+#define TRACE_W0(slot) do { t_panel[(size_t)(nw + 2) + ((size_t)w * G + blockIdx.x) * 8 + (slot)] = gtimer_ns(); } while (0)
 #else
 #define TRACE(slot) do { } while (0)
+#define TRACE_W0(slot) do { } while (0)
+#endif
+/* Sparse / rank-deficient systems: when the first 1024 active rows do not settle a panel,
+ * the pivots must be looked for among ALL active rows.  While a panel that was itself
+ * settled the slow way is swept, the CTAs that update the strip of the next panel word
+ * append every row whose new panel word is non-zero to a candidate list (warp-aggregated
+ * atomics); CTA 0 then scans that list (a few % of the rows on MT19937-class systems)
+ * instead of the whole column.  More than PERSIST_CAND_MAX candidates: full scan. */
+#ifndef PERSIST_CAND_MAX
+#define PERSIST_CAND_MAX 8192
 #endif
 #ifndef PERSIST_TIMEOUT_NS
 #define PERSIST_TIMEOUT_NS 20000000000ULL
@@ -163,31 +175,73 @@ __device__ __forceinline__ bool grid_barrier(GridSync *gs, int *s_ok) {
 /* Look-ahead pivot search, warp 0 only: the 1024 panel words of the first active rows sit in
  * S.qv (slot = row - base8, 0 for rows outside the active range) where the sweep of unit 0
  * left them -- no reload from global memory, no compaction pass.  32 slots at a time; zero
- * words are skipped by ballot; stops as soon as every column of the panel is a pivot. */
+ * words are skipped by ballot; stops as soon as every column of the panel is a pivot.
+ *
+ * The RREF basis is held COLUMN-wise: lane L owns panel columns L and L + 32 as bit masks over
+ * the pivots (bit c of Clo = entry of basis vector c in column L) and rows L and L + 32 of the
+ * transform (bit c of Tlo = "selected row L takes part in E_c").  Reducing a candidate v
+ * against the whole basis is then lane-local -- its bit in column j is
+ * v_j ^ parity(C_j & v & pm) -- and two ballots hand every lane the reduced vector; the only
+ * other cross-lane traffic of an insertion is the broadcast of column c of the basis (which
+ * vectors must absorb the new one to stay reduced).  The REDUX.XOR formulation of
+ * wb_insert measured 210 ns per insertion in this position (profiles/r02_trace.md): with
+ * ~66 insertions per panel on the critical path of EVERY panel it was the longest link of
+ * the chain for n <= 32768 and for the last quarter of the panels of any n. */
 __device__ __forceinline__ void window_search(SelectSmem &S, long long base8, u64 colmask, int lane) {
 	for (int c = lane; c < 64; c += 32) {
 		S.sel[c] = -1;
 		S.topsel[c] = 0;
 	}
-	__syncwarp();
-	WarpBasis W;
-	W.B0 = W.B1 = W.T0 = W.T1 = 0;
-	W.pm = 0;
-	W.nsel = 0;
-	for (int g = 0; g < SWEEP_RU / 32 && W.pm != colmask; g++) {
+	u64 Clo = 0, Chi = 0, Tlo = 0, Thi = 0, pm = 0;
+	int nsel = 0;
+	for (int g = 0; g < SWEEP_RU / 32 && pm != colmask; g++) {
 		const u64 mine = S.qv[32 * g + lane] & colmask;
 		unsigned bal = __ballot_sync(0xffffffffu, mine != 0);
-		while (bal && W.pm != colmask) {
+		while (bal && pm != colmask) {
 			const int src = __ffs((int)bal) - 1;
 			bal &= bal - 1;
-			wb_insert(W, S.sel, shfl64(mine, src), 0, (int)(base8 + 32 * g + src), lane);
+			const u64 v = shfl64(mine, src);
+			const u64 mm = v & pm; /* the basis vectors v picks up */
+			const unsigned vlo = ((unsigned)(v >> lane) & 1u) ^ ((unsigned)__popcll(Clo & mm) & 1u);
+			const unsigned vhi = ((unsigned)(v >> (lane + 32)) & 1u) ^ ((unsigned)__popcll(Chi & mm) & 1u);
+			const u64 vr = (u64)__ballot_sync(0xffffffffu, vlo) | ((u64)__ballot_sync(0xffffffffu, vhi) << 32);
+			if (!vr) continue; /* dependent on the rows selected so far */
+			const int c = __ffsll((long long)vr) - 1;
+			/* transform bits of the new vector: what it picked up, plus itself (selected row nsel) */
+			unsigned tlo = (unsigned)__popcll(Tlo & mm) & 1u, thi = (unsigned)__popcll(Thi & mm) & 1u;
+			if (lane == (nsel & 31)) {
+				if (nsel < 32) tlo ^= 1u;
+				else thi ^= 1u;
+			}
+			/* basis vectors with a 1 in column c absorb the new vector (keeps the basis reduced) */
+			const u64 colc = shfl64(c < 32 ? Clo : Chi, c & 31);
+			const u64 bit = 1ULL << c;
+			Clo = (Clo ^ (vlo ? colc : 0)) | (vlo ? bit : 0);
+			Chi = (Chi ^ (vhi ? colc : 0)) | (vhi ? bit : 0);
+			Tlo = (Tlo ^ (tlo ? colc : 0)) | (tlo ? bit : 0);
+			Thi = (Thi ^ (thi ? colc : 0)) | (thi ? bit : 0);
+			if (lane == 0) S.sel[nsel] = (int)(base8 + 32 * g + src);
+			pm |= bit;
+			nsel++;
 		}
 	}
-	wb_store(W, S.B, S.TB, lane);
-	__syncwarp();
+	/* hand the transform over in the by-pivot-column form select_finalize / the apply read:
+	 * TB[c] bit l = "selected row l takes part in E_c" (a 64 x 64 bit transpose by ballots) */
+	u64 mine_lo = 0, mine_hi = 0;
+#pragma unroll 8
+	for (int c = 0; c < 64; c++) {
+		const u64 wv = (u64)__ballot_sync(0xffffffffu, (unsigned)(Tlo >> c) & 1u) |
+		               ((u64)__ballot_sync(0xffffffffu, (unsigned)(Thi >> c) & 1u) << 32);
+		if (lane == (c & 31)) {
+			if (c < 32) mine_lo = wv;
+			else mine_hi = wv;
+		}
+	}
+	S.TB[lane] = mine_lo;
+	S.TB[lane + 32] = mine_hi;
 	if (lane == 0) {
-		S.pm = W.pm;
-		S.nsel = W.nsel;
+		S.pm = pm;
+		S.nsel = nsel;
 	}
 	__syncwarp();
 }
@@ -263,7 +317,8 @@ static_assert(sizeof(ApplySmem) <= SWEEP_LINES * 128, "the apply scratch aliases
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
 k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2, SolverState *st,
-          long long *hist_r, u64 *hist_pm, GridSync *gs, unsigned long long *t_panel, int w_begin, int w_end) {
+          long long *hist_r, u64 *hist_pm, GridSync *gs, unsigned long long *t_panel, u64 *cand, int w_begin,
+          int w_end) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint4 *TD = reinterpret_cast<uint4 *>(smem_raw);
 	uint4 *E = TD + SWEEP_LINES * 8;
@@ -285,6 +340,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 	}
 	__syncthreads();
 	unsigned phase = 0;
+	bool list_ready = false; /* the candidate list of the panel about to start was collected */
 
 	for (int w = w_begin; w < w_end; ++w) {
 		u64 *pc_cur = (w & 1) ? pc1 : pc0, *pc_next = (w & 1) ? pc0 : pc1;
@@ -296,21 +352,37 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 
 		/* ---- slow path: nobody settled this panel ahead of time ---------------- */
 		uint4 hd = __ldcg(&gs->hdr[w & 1]);
-		if ((int)hd.x != w + 1) {
+		const bool slow = (int)hd.x != w + 1;
+		if (slow) {
 			u64 colmask = ~0ULL;
 			if (w == nw - 1 && (M.n & 63)) colmask = (1ULL << (M.n & 63)) - 1;
 			if (blockIdx.x == 0) {
 				const long long r = *(volatile long long *)&st->r;
+				const unsigned cnt = list_ready ? *(volatile unsigned *)&gs->cand_cnt[w & 1] : 0xffffffffu;
 				select_init(S);
 				__syncthreads();
-				select_scan(S, pc_cur, r, m, colmask);
+				if (cnt <= PERSIST_CAND_MAX)
+					select_scan(S, pc_cur, 0, (long long)cnt, colmask, cand + (size_t)(w & 1) * PERSIST_CAND_MAX * 2);
+				else
+					select_scan(S, pc_cur, r, m, colmask);
 				if (tid < 32) {
 					select_finalize(S, pc_cur, w, r, st, pd, hist_r, hist_pm);
 					__syncwarp();
-					if (tid == 0) hdr_publish(gs, w, r + S.nsel, S.pm);
+					if (tid == 0) {
+						hdr_publish(gs, w, r + S.nsel, S.pm);
+						__threadfence();
+						st_release_gpu(&gs->sel_flag, (unsigned)w + 1);
+					}
 				}
 			}
-			if (!grid_barrier(gs, s_ok)) return;
+			/* every CTA: wait for the description, apply its share of the strips, ONE barrier */
+			__syncthreads();
+			if (tid == 0) {
+				const bool ok = persist_wait(&gs->sel_flag, (unsigned)w + 1, nullptr, gs);
+				*s_state = ok ? 1 : 0;
+			}
+			__syncthreads();
+			if (*s_state == 0) return;
 			const int s0a = w >> SW_SHIFT;
 			const int mine = (M.ns - s0a - (int)blockIdx.x + G - 1) / G; /* strips s0a + b + i*G */
 			persist_apply(M, pd, const_cast<uint4 *>(ebuf), AP, mine > 0 ? mine : 0,
@@ -318,6 +390,11 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 			if (!grid_barrier(gs, s_ok)) return;
 			hd = __ldcg(&gs->hdr[w & 1]);
 		}
+		/* the list of this panel is consumed (or was not needed); its slot is refilled two panels on */
+		if (blockIdx.x == 0 && tid == 0) gs->cand_cnt[w & 1] = 0;
+		/* collect candidates for the next panel while sweeping a panel that needed the slow path */
+		const bool collect = slow;
+		list_ready = false;
 
 		const long long r1 = (long long)hd.y;
 		const u64 pm = ((u64)hd.w << 32) | hd.z;
@@ -447,6 +524,29 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 						if (has_next && u == 0) S.qv[rl + (SWEEP_THREADS / SQ) * q] = nv; /* for the look-ahead search */
 					}
 				}
+				if (force && collect && has_next) {
+					/* (uniform branch, sparse / rank-deficient systems only) warp-aggregated append of
+					 * {row, new panel word} to the next panel's candidate list; the words are read back
+					 * from pc_next, where this thread stored them a moment ago (same thread: ordered) */
+#pragma unroll
+					for (int q = 0; q < SWEEP_U; q++) {
+						const long long row = row0 + (SWEEP_THREADS / SQ) * q;
+						const u64 nvq = (ch == nch && row >= r1 && row < m) ? (__ldcg(pc_next + row) & colmask_next) : 0;
+						const unsigned bal = __ballot_sync(0xffffffffu, nvq != 0);
+						if (bal) {
+							const int lane = tid & 31, leader = __ffs((int)bal) - 1;
+							unsigned base_i = 0;
+							if (lane == leader) base_i = atomicAdd(&gs->cand_cnt[wn & 1], (unsigned)__popc(bal));
+							base_i = __shfl_sync(0xffffffffu, base_i, leader);
+							const unsigned idx = base_i + __popc(bal & ((1u << lane) - 1));
+							if (nvq && idx < PERSIST_CAND_MAX) {
+								u64 *ce = cand + ((size_t)(wn & 1) * PERSIST_CAND_MAX + idx) * 2;
+								__stcg(ce, (u64)row);
+								__stcg(ce + 1, nvq);
+							}
+						}
+					}
+				}
 				if (has_next && u == 0) {
 					/* look-ahead: this CTA just produced word w+1 of the first active rows; search
 					 * them for the next panel's pivots while the other SMs keep streaming */
@@ -456,9 +556,11 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 					if (tid < 32) {
 						const long long lim = min(m, base8 + (long long)SWEEP_RU);
 						window_search(S, base8, colmask_next, tid);
+						TRACE_W0(1); /* (the search CTA's slot 1 is re-used: window search done) */
 						const bool final_ = (S.pm == colmask_next || lim == m);
 						if (final_) select_finalize(S, pc_next, wn, r1, st, pdn, hist_r, hist_pm);
 						__syncwarp();
+						TRACE_W0(0); /* (slot 0 re-used by the search CTA: finalize done) */
 						if (tid == 0) {
 							if (final_) hdr_publish(gs, wn, r1 + S.nsel, S.pm);
 							__threadfence();
@@ -471,6 +573,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 			}
 		}
 
+		list_ready = collect && has_next;
 		/* ---- apply(w+1) for the strips whose first-rows unit this CTA swept ------- */
 		TRACE(2); /* my units are done */
 		if (has_next) {

@@ -21,8 +21,17 @@ def rng(a, b):
             "units_mean": rel(2, np.nanmean), "units_max": rel(2, np.nanmax), "flag_max": rel(3, np.nanmax),
             "apply_mean": rel(4, np.nanmean), "apply_max": rel(4, np.nanmax), "barrier_max": rel(5, np.nanmax),
             "srch_start": rel(6, np.nanmax), "srch_end": rel(7, np.nanmax)}
+# the search CTA (the one with a non-zero slot 6) re-uses its slots 1 / 0: window search done / finalize done
+srch = tr[:, :, 6] > 0
+def srch_phase(a, b):
+    sl = tr[a:b]; m_ = srch[a:b]
+    if not m_.any(): return None
+    t6 = sl[:, :, 6][m_].astype(float); t1 = sl[:, :, 1][m_].astype(float); t0 = sl[:, :, 0][m_].astype(float); t7 = sl[:, :, 7][m_].astype(float)
+    return {"window_search": np.mean(t1 - t6) / 1e3, "finalize": np.mean(t0 - t1) / 1e3, "fence+release+sync": np.mean(t7 - t0) / 1e3}
 step = max(1, nw // 8)
 for a in range(0, nw - 1, step):
     b = min(nw - 1, a + step)
     o = rng(a, b)
     print(f"panels {a:5d}-{b:5d}: " + " ".join(f"{k}={v:7.2f}" for k, v in o.items()))
+    sp = srch_phase(a, b)
+    if sp: print("      search CTA: " + " ".join(f"{k}={v:6.2f}" for k, v in sp.items()))
