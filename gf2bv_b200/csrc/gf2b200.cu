@@ -57,6 +57,14 @@ struct gf2b200_ctx {
 	int persist;     /* the one-kernel forward elimination (k_forward) can be launched cooperatively */
 	ncclComm_t nccl; /* nccl contexts */
 	struct gf2b200_system *cached; /* device buffers of the last gf2b200_solve, reused for equal shapes */
+	/* host-buffer loads: staging buffers, copy stream and events live as long as the context
+	 * (an MT19937-class API solve is ~20 ms: allocating these per call showed) */
+	u64 *stage[2];
+	size_t stage_bytes;
+	u64 *d_bstage;
+	size_t bstage_bytes;
+	cudaStream_t copy_stream;
+	cudaEvent_t ev_copied[2], ev_laid[2];
 	char err[512];
 };
 
@@ -186,6 +194,7 @@ static int ctx_init(gf2b200_ctx **out, int device) {
 	c->n_sm = prop.multiProcessorCount;
 	c->stream = c->own_stream;
 	e = cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM);
 	/* Tuning switch (off by default, not yet A/B-ed): GF2B200_CARVEOUT=<percent> asks for the
 	 * same shared-memory carve-out in the small per-panel kernels as k_sweep gets (164 of
 	 * 228 KiB = 72), so that the SMs are not re-partitioned three times per panel. */
@@ -273,6 +282,14 @@ extern "C" void gf2b200_destroy(gf2b200_ctx *ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->cached) gf2b200_system_destroy(ctx->cached);
+	cudaFree(ctx->stage[0]);
+	cudaFree(ctx->stage[1]);
+	cudaFree(ctx->d_bstage);
+	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+	for (int i = 0; i < 2; i++) {
+		if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+		if (ctx->ev_laid[i]) cudaEventDestroy(ctx->ev_laid[i]);
+	}
 	if (ctx->nccl) g_nccl.CommDestroy(ctx->nccl);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
 	free(ctx);
@@ -543,25 +560,48 @@ extern "C" int gf2b200_system_load_host(gf2b200_system *sys, const uint64_t *A, 
 	const long long m_loc = gf2b200_system_local_rows(sys);
 	const long long base = sys->sh[0].row_begin;
 	/* rows travel in chunks through two device staging buffers: the copy of chunk
-	 * c+1 (copy stream) overlaps the layout kernel of chunk c (solver stream) */
+	 * c+1 (copy stream) overlaps the layout kernel of chunk c (solver stream).  Buffers,
+	 * stream and events belong to the context and are reused by every load. */
 	const size_t row_bytes = (size_t)stride64 * 8;
 	long long chunk_rows = std::max<long long>(1, (long long)((64u << 20) / row_bytes));
 	chunk_rows = std::min<long long>(chunk_rows, std::max<long long>(m_loc, 1));
-	u64 *stage[2] = {nullptr, nullptr};
-	u64 *d_b = nullptr;
-	cudaStream_t copy_stream = nullptr;
-	cudaEvent_t copied[2] = {nullptr, nullptr}, laid[2] = {nullptr, nullptr};
-	int rc = GF2B200_OK;
-	cudaError_t e = cudaMalloc(&stage[0], chunk_rows * row_bytes);
-	if (e == cudaSuccess && chunk_rows < m_loc) e = cudaMalloc(&stage[1], chunk_rows * row_bytes);
-	if (e == cudaSuccess && b) e = cudaMalloc(&d_b, (size_t)((m_loc + 63) / 64) * 8);
-	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
-	for (int i = 0; i < 2 && e == cudaSuccess; i++) {
-		e = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
-		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&laid[i], cudaEventDisableTiming);
+	const size_t need = (size_t)chunk_rows * row_bytes;
+	const bool two = chunk_rows < m_loc;
+	cudaError_t e = cudaSuccess;
+	if (ctx->stage_bytes < need || (two && !ctx->stage[1])) {
+		cudaFree(ctx->stage[0]);
+		cudaFree(ctx->stage[1]);
+		ctx->stage[0] = ctx->stage[1] = nullptr;
+		ctx->stage_bytes = 0;
+		e = cudaMalloc(&ctx->stage[0], need);
+		if (e == cudaSuccess && two) e = cudaMalloc(&ctx->stage[1], need);
+		if (e == cudaSuccess) ctx->stage_bytes = need;
 	}
+	const size_t b_bytes = (size_t)((m_loc + 63) / 64) * 8;
+	if (e == cudaSuccess && b && ctx->bstage_bytes < b_bytes) {
+		cudaFree(ctx->d_bstage);
+		ctx->d_bstage = nullptr;
+		ctx->bstage_bytes = 0;
+		e = cudaMalloc(&ctx->d_bstage, b_bytes);
+		if (e == cudaSuccess) ctx->bstage_bytes = b_bytes;
+	}
+	if (e == cudaSuccess && !ctx->copy_stream) {
+		e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+		for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+			e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_laid[i], cudaEventDisableTiming);
+		}
+	}
+	u64 **stage = ctx->stage;
+	u64 *d_b = b ? ctx->d_bstage : nullptr;
+	cudaStream_t copy_stream = ctx->copy_stream;
+	cudaEvent_t *copied = ctx->ev_copied, *laid = ctx->ev_laid;
+	int rc = GF2B200_OK;
+	/* the previous load's last layout kernels may still be reading the staging buffers */
+	if (e == cudaSuccess) e = cudaEventRecord(laid[0], ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, laid[0], 0);
 	if (e == cudaSuccess && b)
-		e = cudaMemcpyAsync(d_b, b, (size_t)((m_loc + 63) / 64) * 8, cudaMemcpyHostToDevice, ctx->stream);
+		e = cudaMemcpyAsync(d_b, b, b_bytes, cudaMemcpyHostToDevice, ctx->stream);
 	int ci = 0, used[2] = {0, 0};
 	for (Shard &h : sys->sh) {
 		const long long off = h.row_begin - base;
@@ -585,18 +625,15 @@ extern "C" int gf2b200_system_load_host(gf2b200_system *sys, const uint64_t *A, 
 			ci ^= 1;
 		}
 	}
-	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-	if (e != cudaSuccess) rc = fail(ctx, GF2B200_ECUDA, "system_load_host: %s", cudaGetErrorString(e));
-	if (copy_stream) {
+	/* the caller's host buffers are free again once every copy has left them; the layout
+	 * kernels still in flight are ordered before whatever the caller enqueues next on the
+	 * solver stream (gf2b200_system_eliminate) */
+	if (e == cudaSuccess) e = cudaStreamSynchronize(copy_stream);
+	if (e == cudaSuccess && b) e = cudaStreamSynchronize(ctx->stream); /* b travels on the solver stream */
+	if (e != cudaSuccess) {
+		rc = fail(ctx, GF2B200_ECUDA, "system_load_host: %s", cudaGetErrorString(e));
 		cudaStreamSynchronize(copy_stream);
-		cudaStreamDestroy(copy_stream);
-	}
-	cudaFree(stage[0]);
-	cudaFree(stage[1]);
-	cudaFree(d_b);
-	for (int i = 0; i < 2; i++) {
-		if (copied[i]) cudaEventDestroy(copied[i]);
-		if (laid[i]) cudaEventDestroy(laid[i]);
+		cudaStreamSynchronize(ctx->stream);
 	}
 	sys->eliminated = 0;
 	return rc;
@@ -725,32 +762,53 @@ static int forward_sharded(gf2b200_system *sys, long long *launches, double *xby
 		Shard &h0 = sys->sh[0];
 		NK(ctx, g_nccl.AllGather(h0.d_slab, h0.d_slab_all, 8, ncclUint8, ctx->nccl, st));
 	}
+	/* Per panel and shard: [k_select_publish] [k_elect] k_apply_pull k_apply_commit k_sweep_dist.
+	 * The first two are no-ops whenever the PREVIOUS sweep's look-ahead already published this
+	 * shard's candidates and (one process per GPU) ran the election: the pivot exchange of
+	 * panel w+1 then overlaps the sweep of panel w, and what is left between two sweeps is the
+	 * pull of the elected rows over NVLink, one flag round (nobody overwrites an elected row
+	 * before every peer has pulled it) and the commit. */
+	const bool look = !getenv("GF2B200_NO_DIST_LOOKAHEAD"); /* diagnostic switch */
+	/* the look-ahead CTA of a sweep runs the local search (~17 us), waits for the peers' candidate
+	 * blocks and runs the election (~15-30 us): it is spared that many work units (3.3 us each) */
+	int dist_pad = barriers ? 24 : SWEEP_SEL_PAD;
+	if (const char *dp = getenv("GF2B200_DIST_PAD")) dist_pad = atoi(dp);
 	for (int w = 0; w < nw; w++) {
 		u64 colmask = ~0ULL;
 		if (w == nw - 1 && (sys->n & 63)) colmask = (1ULL << (sys->n & 63)) - 1;
+		u64 colmask_next = ~0ULL;
+		if (w + 1 == nw - 1 && (sys->n & 63)) colmask_next = (1ULL << (sys->n & 63)) - 1;
 		const int s0a = w >> SW_SHIFT, nsr = ns - s0a;
 		const unsigned epoch = sys->epoch_base + (unsigned)w + 1;
 		for (Shard &h : sys->sh)
-			k_select_publish<<<1, SEL_THREADS, 0, st>>>(h.M, h.d_pc[w & 1], colmask, h.d_state, h.d_pt, h.index, G,
+			k_select_publish<<<1, SEL_THREADS, 0, st>>>(h.M, h.d_pc[w & 1], w, colmask, h.d_state, h.d_pt, h.index, G,
 			                                            epoch, barriers);
 		for (Shard &h : sys->sh)
-			k_elect<<<1, 32, 0, st>>>(h.xch, G, h.index, w, colmask, h.d_state, h.d_pd, h.d_dp, h.d_pc[w & 1],
+			k_elect<<<1, 32, 0, st>>>(h.xch, G, h.index, w, colmask, h.d_state, h.d_pd + (w & 1), h.d_dp, h.d_pc[w & 1],
 			                          h.d_hist_r, h.d_hist_pm, h.d_hist_owner, epoch, barriers);
 		for (Shard &h : sys->sh)
-			k_apply_pull<<<std::min(nsr, apply_cap), APPLY_THREADS, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_pt, h.d_ebuf, s0a, h.d_state);
-		if (barriers)
-			for (Shard &h : sys->sh) {
-				k_peer_barrier<<<1, 64, 0, st>>>(h.xch, h.d_pt, h.index, G, epoch, h.d_state);
-				(*launches)++;
-			}
+			k_apply_pull<<<std::min(nsr, apply_cap), APPLY_THREADS, 0, st>>>(h.M, h.d_pd + (w & 1), h.d_dp, h.d_pt, h.d_ebuf,
+			                                                                s0a, h.d_state, h.index, G, epoch, barriers);
 		int li = 0;
 		for (Shard &h : sys->sh) {
-			k_apply_commit<<<std::min(nsr, apply_cap), APPLY_THREADS, 0, st>>>(h.M, h.d_pd, h.d_dp, h.d_ebuf, s0a, h.d_state);
+			k_apply_commit<<<std::min(nsr, apply_cap), APPLY_THREADS, 0, st>>>(h.M, h.d_pd + (w & 1), h.d_dp, h.d_ebuf, s0a,
+			                                                                  h.d_state, h.xch, G, epoch, barriers);
 			const bool ev = prof && li == 0;
 			if (ev) CK(ctx, cudaEventRecord(sys->ev[6 + 2 * w], st));
-			k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(h.M, h.d_pd, h.d_pc[w & 1],
-			                                                     h.d_pc[(w + 1) & 1], h.d_ebuf, w,
-			                                                     (w + 1) >> SW_SHIFT, nullptr, nullptr, nullptr, nullptr, 0);
+			DistLook dl;
+			dl.pt = h.d_pt;
+			dl.xch = h.xch;
+			dl.dp = h.d_dp;
+			dl.hist_owner = h.d_hist_owner;
+			dl.me = h.index;
+			dl.G = G;
+			dl.epoch_next = epoch + 1;
+			dl.barriers = barriers;
+			dl.pad = dist_pad;
+			PanelDesc *pdn = (look && w + 1 < nw) ? h.d_pd + ((w + 1) & 1) : nullptr;
+			k_sweep_dist<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(h.M, h.d_pd + (w & 1), h.d_pc[w & 1],
+			                                                          h.d_pc[(w + 1) & 1], h.d_ebuf, w, (w + 1) >> SW_SHIFT,
+			                                                          pdn, h.d_state, h.d_hist_r, h.d_hist_pm, colmask_next, dl);
 			if (ev) CK(ctx, cudaEventRecord(sys->ev[7 + 2 * w], st));
 			li++;
 		}

@@ -49,6 +49,7 @@ namespace gf2b200 {
 struct XchBlock {
 	unsigned flagA[MAX_SHARDS]; /* epoch of the last candidate block published by src */
 	unsigned flagB[MAX_SHARDS]; /* epoch up to which src has pulled its pivot rows */
+	unsigned flagC[MAX_SHARDS]; /* epoch of the last panel whose sweep src has COMPLETED (its rows may be pulled) */
 	u64 cand[MAX_SHARDS][CAND_W];
 };
 
@@ -103,33 +104,42 @@ __device__ __forceinline__ bool wait_flag(const unsigned *flag, unsigned epoch) 
 	return true;
 }
 
+/* What the sweep of a sharded system needs for its look-ahead (passed by pointer to a
+ * kernel-parameter copy). */
+struct DistLook {
+	const PeerTable *pt;
+	XchBlock *xch;
+	DistPanel *dp;
+	unsigned char *hist_owner;
+	int me, G;
+	unsigned epoch_next; /* flag epoch of the NEXT panel's candidate blocks */
+	int barriers;        /* 1: one process per GPU (flag waits); 0: loopback shards on one stream */
+	int pad;             /* work units the look-ahead CTA is spared */
+};
+__device__ __forceinline__ int dist_sel_pad(const DistLook *dl) { return dl->pad; }
+
 /* ------------------------------------------------------------------------
- * k_select_publish: candidates of one shard for the current panel word, stored
- * into every peer's exchange block (slot `me`), then flag A.
+ * publish_candidates (all threads of a CTA): the <= 64 rows S.sel[] that the scan selected
+ * form a basis of this shard's active panel words; their raw panel words + row numbers go
+ * into slot `me` of every peer's exchange block, then flag A.
  * block = [count | 64 raw panel words | 64 local row numbers as ints | pad]
  * ---------------------------------------------------------------------- */
-__global__ void __launch_bounds__(SEL_THREADS, 1)
-k_select_publish(Mat M, const u64 *__restrict__ pc, u64 colmask, const SolverState *st,
-                 const PeerTable *__restrict__ pt, int me, int G, unsigned epoch, int barriers) {
-	__shared__ SelectSmem S;
-	__shared__ u64 blk[CAND_W];
+__device__ __forceinline__ void publish_candidates(SelectSmem &S, u64 *blk, const u64 *pc, u64 colmask,
+                                                   const PeerTable *__restrict__ pt, int me, int G, unsigned epoch,
+                                                   int barriers) {
 	const int tid = threadIdx.x;
-	if (*(const volatile int *)&st->fault) return; /* an earlier wait timed out: the elimination is void */
-	select_init(S);
-	__syncthreads();
-	select_scan(S, pc, st->r_loc, M.m, colmask);
 	if (tid < CAND_W) blk[tid] = 0;
 	__syncthreads();
 	if (tid < 64) {
 		const int n = S.nsel;
 		if (tid < n) {
-			blk[1 + tid] = pc[S.sel[tid]] & colmask;
+			blk[1 + tid] = __ldcg(pc + S.sel[tid]) & colmask;
 			reinterpret_cast<int *>(blk + 65)[tid] = S.sel[tid];
 		}
 		if (tid == 0) blk[0] = (u64)n;
 	}
 	__syncthreads();
-	for (int t = tid; t < G * CAND_W; t += SEL_THREADS) {
+	for (int t = tid; t < G * CAND_W; t += blockDim.x) {
 		const int g = t / CAND_W, i = t - g * CAND_W;
 		pt->xch[g]->cand[me][i] = blk[i];
 	}
@@ -138,18 +148,32 @@ k_select_publish(Mat M, const u64 *__restrict__ pc, u64 colmask, const SolverSta
 	if (barriers && tid < G) st_release_sys(&pt->xch[tid]->flagA[me], epoch);
 }
 
+/* k_select_publish: the full scan of this shard's active rows + publish.  A no-op when the
+ * previous sweep's look-ahead already published this panel's candidates. */
+__global__ void __launch_bounds__(SEL_THREADS, 1)
+k_select_publish(Mat M, const u64 *__restrict__ pc, int w, u64 colmask, SolverState *st,
+                 const PeerTable *__restrict__ pt, int me, int G, unsigned epoch, int barriers) {
+	__shared__ SelectSmem S;
+	__shared__ u64 blk[CAND_W];
+	if (*(const volatile int *)&st->fault) return; /* an earlier wait timed out: the elimination is void */
+	if (*(const volatile int *)&st->published == w + 1) return;
+	select_init(S);
+	__syncthreads();
+	select_scan(S, pc, st->r_loc, M.m, colmask);
+	publish_candidates(S, blk, pc, colmask, pt, me, G, epoch, barriers);
+}
+
 /* ------------------------------------------------------------------------
- * k_elect: global pivot election, one warp, identical on every shard.
- * Candidate code = shard * 64 + slot.
+ * elect_body: global pivot election, ONE WARP, identical on every shard.
+ * Candidate code = shard * 64 + slot.  Scratch: S.B, S.TB, S.sel, S.topsel, S.mv_src, S.mv_dst.
  * ---------------------------------------------------------------------- */
-__global__ void __launch_bounds__(32)
-k_elect(const XchBlock *__restrict__ xch, int G, int me, int w, u64 colmask, SolverState *st,
-        PanelDesc *pd, DistPanel *dp, u64 *__restrict__ pc, long long *hist_r, u64 *hist_pm,
-        unsigned char *hist_owner, unsigned epoch, int barriers) {
-	__shared__ u64 B[64], TB[64];
-	__shared__ int sel[64];
-	__shared__ int topsel[64], mv_src[64], mv_dst[64];
-	const int lane = threadIdx.x;
+__device__ __forceinline__ void elect_body(SelectSmem &S, const XchBlock *__restrict__ xch, int G, int me, int w,
+                                           u64 colmask, SolverState *st, PanelDesc *pd, DistPanel *dp,
+                                           u64 *__restrict__ pc, long long *hist_r, u64 *hist_pm,
+                                           unsigned char *hist_owner, unsigned epoch, int barriers) {
+	u64 *B = S.B, *TB = S.TB;
+	int *sel = S.sel, *topsel = S.topsel, *mv_src = S.mv_src, *mv_dst = S.mv_dst;
+	const int lane = threadIdx.x & 31;
 	if (*(volatile int *)&st->fault) return;
 	if (barriers) {
 		bool ok = true;
@@ -178,10 +202,10 @@ k_elect(const XchBlock *__restrict__ xch, int G, int me, int w, u64 colmask, Sol
 		for (int jj = 0; jj < G && W.pm != colmask; jj++) {
 			const int src = (w + jj) % G;
 			const u64 *cb = xch->cand[src];
-			const int cnt = (int)cb[0];
+			const int cnt = (int)__ldcg(cb);
 			const int nq = min(per, cnt - q0); /* per <= 32: one candidate per lane */
 			if (nq <= 0) continue;
-			const u64 mine = (lane < nq) ? cb[1 + q0 + lane] : 0;
+			const u64 mine = (lane < nq) ? __ldcg(cb + 1 + q0 + lane) : 0;
 			for (int j = 0; j < nq && W.pm != colmask; j++)
 				wb_insert(W, sel, shfl64(mine, j), 0, src * 64 + q0 + j, lane);
 		}
@@ -196,7 +220,7 @@ k_elect(const XchBlock *__restrict__ xch, int G, int me, int w, u64 colmask, Sol
 		pd->sel[c] = sel[c];
 		const int src = (c < k) ? (sel[c] >> 6) : -1;
 		dp->src[c] = src;
-		dp->srow[c] = (c < k) ? reinterpret_cast<const int *>(xch->cand[src] + 65)[sel[c] & 63] : -1;
+		dp->srow[c] = (c < k) ? __ldcg(reinterpret_cast<const int *>(xch->cand[src] + 65) + (sel[c] & 63)) : -1;
 		hist_owner[(long long)w * 64 + c] = (c < k) ? (unsigned char)src : 0xFF;
 	}
 	__syncwarp();
@@ -238,13 +262,13 @@ k_elect(const XchBlock *__restrict__ xch, int G, int me, int w, u64 colmask, Sol
 	u64 tmpv[2];
 	for (int h = 0; h < 2; h++) {
 		const int q = lane + 32 * h;
-		tmpv[h] = (q < ndis) ? pc[mv_src[q]] : 0;
+		tmpv[h] = (q < ndis) ? __ldcg(pc + mv_src[q]) : 0;
 	}
 	__syncwarp();
 	for (int h = 0; h < 2; h++) {
 		const int q = lane + 32 * h;
 		if (q < ndis) {
-			pc[mv_dst[q]] = tmpv[h];
+			__stcg(pc + mv_dst[q], tmpv[h]);
 			pd->mv_src[q] = mv_src[q];
 			pd->mv_dst[q] = mv_dst[q];
 		}
@@ -258,9 +282,40 @@ k_elect(const XchBlock *__restrict__ xch, int G, int me, int w, u64 colmask, Sol
 		pd->pm = pm;
 		st->r += k;
 		st->r_loc = r_loc + my_cnt;
+		st->elected = w + 1;
 		hist_r[w] = r_loc;
 		hist_pm[w] = pm;
 	}
+}
+
+/* k_elect: one warp.  A no-op when the previous sweep's look-ahead already ran this election. */
+__global__ void __launch_bounds__(32)
+k_elect(const XchBlock *__restrict__ xch, int G, int me, int w, u64 colmask, SolverState *st,
+        PanelDesc *pd, DistPanel *dp, u64 *__restrict__ pc, long long *hist_r, u64 *hist_pm,
+        unsigned char *hist_owner, unsigned epoch, int barriers) {
+	__shared__ SelectSmem S;
+	if (*(volatile int *)&st->elected == w + 1) return;
+	elect_body(S, xch, G, me, w, colmask, st, pd, dp, pc, hist_r, hist_pm, hist_owner, epoch, barriers);
+}
+
+/* The sweep's look-ahead on a sharded system (called by every thread of the CTA that just swept
+ * the first active rows; S holds the scan of their new panel words).  If those rows settle this
+ * shard's part (full local rank, or no more rows): publish the candidates; and when every rank
+ * is its own process, wait for the peers' blocks and run the election here, so that the panel's
+ * description is ready before the sweep ends.  Otherwise k_select_publish / k_elect do it. */
+__device__ __forceinline__ void dist_lookahead(const DistLook *dl, SelectSmem &S, u64 *pc_next, int wn,
+                                               u64 colmask_next, long long r1, long long lim, long long m,
+                                               SolverState *st, PanelDesc *pd_next, long long *hist_r, u64 *hist_pm) {
+	const int tid = threadIdx.x;
+	const bool final_ = (S.pm == colmask_next || lim == m); /* uniform: read after the scan's barrier */
+	__syncthreads();
+	if (!final_) return;
+	/* the candidate block is staged in the scan's (now idle) queue */
+	publish_candidates(S, S.qv, pc_next, colmask_next, dl->pt, dl->me, dl->G, dl->epoch_next, dl->barriers);
+	if (tid == 0) st->published = wn + 1;
+	if (dl->barriers && tid < 32)
+		elect_body(S, dl->xch, dl->G, dl->me, wn, colmask_next, st, pd_next, dl->dp, pc_next, hist_r, hist_pm,
+		           dl->hist_owner, dl->epoch_next, 1);
 }
 
 /* ------------------------------------------------------------------------
@@ -270,13 +325,26 @@ k_elect(const XchBlock *__restrict__ xch, int G, int me, int w, u64 colmask, Sol
  * ---------------------------------------------------------------------- */
 __global__ void __launch_bounds__(APPLY_THREADS)
 k_apply_pull(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restrict__ dp,
-             const PeerTable *__restrict__ pt, uint4 *__restrict__ ebuf, int s0, const SolverState *st) {
+             const PeerTable *__restrict__ pt, uint4 *__restrict__ ebuf, int s0, SolverState *st, int me, int G,
+             unsigned epoch, int barriers) {
 	__shared__ uint4 Sel[64][SQ];
 	__shared__ u64 sTB[64];
+	__shared__ int s_last, s_okc;
 	if (*(const volatile int *)&st->fault) return;
 	const int k = pd->k;
-	if (k == 0) return;
+	if (barriers && k > 0) {
+		/* every owner has finished sweeping the previous panel (flag C) before its rows are read */
+		if (threadIdx.x == 0) s_okc = 1;
+		__syncthreads();
+		if ((int)threadIdx.x < G && !wait_flag(&pt->xch[me]->flagC[threadIdx.x], epoch - 1)) {
+			s_okc = 0;
+			st->fault = 1;
+		}
+		__syncthreads();
+		if (!s_okc) return;
+	}
 	const int tid = threadIdx.x, rr = tid / SQ, ch = tid % SQ;
+	if (k > 0) {
 	if (tid < 64) sTB[tid] = pd->TB[tid];
 	const uint4 *prow = nullptr; /* my elected row's piece of strip 0 on its owner */
 	long long pstride = 0;       /* uint4 per strip there */
@@ -300,34 +368,67 @@ k_apply_pull(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restric
 		ebuf[(long long)s * EBUF_Q + rr * SQ + ch] = acc;
 		__syncthreads();
 	}
+	}
+	/* flag B ("this shard has pulled its pivot rows of the panel"): the last CTA to finish tells
+	 * every peer; k_apply_commit waits for all of them before an elected row is overwritten */
+	if (!barriers) return;
+	__syncthreads();
+	if (tid == 0) {
+		__threadfence();
+		s_last = (atomicAdd(&st->pull_cnt, 1u) == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (!s_last) return;
+	if (tid == 0) st->pull_cnt = 0;
+	__threadfence_system();
+	if (tid < G) st_release_sys(&pt->xch[tid]->flagB[me], epoch);
 }
 
-/* flag B: signal "I have pulled my pivot rows of this panel" to every peer and
- * wait until every peer has done the same */
-__global__ void __launch_bounds__(64)
-k_peer_barrier(XchBlock *xch, const PeerTable *__restrict__ pt, int me, int G, unsigned epoch,
-               SolverState *st) {
-	const int g = threadIdx.x;
-	if (*(volatile int *)&st->fault) return;
+/* k_sweep on the local rows of a shard, with the sharded look-ahead (publish + election of the
+ * next panel from inside the sweep) */
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+k_sweep_dist(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur, u64 *__restrict__ pc_next,
+             const uint4 *__restrict__ ebuf, int w, int s0, PanelDesc *pd_next, SolverState *st, long long *hist_r,
+             u64 *hist_pm, u64 colmask_next, DistLook dl) {
+	sweep_body(M, pd, pc_cur, pc_next, ebuf, w, s0, pd_next, st, hist_r, hist_pm, colmask_next, &dl);
+	/* Flag C.  With the look-ahead a peer learns which of this shard's rows were elected for
+	 * panel w+1 while this sweep is still running; it may pull them only once EVERY strip of
+	 * them has been swept: the last CTA to finish tells every peer "sweep of panel w done". */
+	if (!dl.barriers) return;
+	__shared__ int is_last;
+	__threadfence_system(); /* this thread's row stores, visible to the peers, before the CTA's ticket */
+	__syncthreads();
+	if (threadIdx.x == 0) is_last = (atomicAdd(&st->sweep_done, 1u) == gridDim.x - 1);
+	__syncthreads();
+	if (!is_last) return;
+	if (threadIdx.x == 0) st->sweep_done = 0;
 	__threadfence_system();
-	bool ok = true;
-	if (g < G) {
-		st_release_sys(&pt->xch[g]->flagB[me], epoch);
-		ok = wait_flag(&xch->flagB[g], epoch);
-	}
-	if (!ok) st->fault = 1;
+	if ((int)threadIdx.x < dl.G) st_release_sys(&dl.pt->xch[threadIdx.x]->flagC[dl.me], dl.epoch_next - 1);
 }
 
 /* k_apply_commit: the owner of elected row j stores E_j (from ebuf) at local row
  * r + (index among its own); displaced rows go to the vacated positions */
 __global__ void __launch_bounds__(APPLY_THREADS)
 k_apply_commit(Mat M, const PanelDesc *__restrict__ pd, const DistPanel *__restrict__ dp,
-               const uint4 *__restrict__ ebuf, int s0, const SolverState *st) {
+               const uint4 *__restrict__ ebuf, int s0, SolverState *st, const XchBlock *xch, int G, unsigned epoch,
+               int barriers) {
 	__shared__ uint4 Dis[64][SQ];
 	__shared__ int ssrc[64], sdst[64], smyidx[64];
+	__shared__ int s_ok;
 	if (*(const volatile int *)&st->fault) return;
 	const int k = pd->k;
 	if (k == 0) return;
+	if (barriers) {
+		/* nobody overwrites an elected row before every peer has pulled it */
+		if (threadIdx.x == 0) s_ok = 1;
+		__syncthreads();
+		if (threadIdx.x < G && !wait_flag(&xch->flagB[threadIdx.x], epoch)) {
+			s_ok = 0;
+			st->fault = 1;
+		}
+		__syncthreads();
+		if (!s_ok) return;
+	}
 	const int tid = threadIdx.x, rr = tid / SQ, ch = tid % SQ;
 	const long long r = pd->r;
 	const int nmove = pd->nmove;

@@ -95,7 +95,18 @@ struct SolverState {
 	int inconsistent;
 	int fault;       /* a peer-memory flag wait timed out */
 	unsigned sweep_done; /* SWEEP_TAIL_SELECT: CTAs of the running sweep that have finished */
+	/* row-sharded systems (gf2b200_dist.cuh): panel + 1 whose candidates this shard has already
+	 * published / whose election it has already run from inside the previous sweep, and the
+	 * CTA counter of the pivot-row pull */
+	int published, elected;
+	unsigned pull_cnt;
 };
+
+struct DistLook; /* look-ahead of the sharded path inside the sweep (gf2b200_dist.cuh) */
+__device__ __forceinline__ int dist_sel_pad(const DistLook *dl);
+__device__ __forceinline__ void dist_lookahead(const DistLook *dl, struct SelectSmem &S, u64 *pc_next, int wn,
+                                               u64 colmask_next, long long r1, long long lim, long long m,
+                                               SolverState *st, PanelDesc *pd_next, long long *hist_r, u64 *hist_pm);
 
 __host__ __device__ __forceinline__ u64 mix64(u64 z) {
 	z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
@@ -739,7 +750,8 @@ static_assert(SWEEP_THREADS == 8 * 32 * 4, "one partial-table item per thread; (
 __device__ __forceinline__ void
 sweep_body(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
            u64 *__restrict__ pc_next, const uint4 *__restrict__ ebuf, int w, int s0,
-           PanelDesc *pd_next, SolverState *st, long long *hist_r, u64 *hist_pm, u64 colmask_next) {
+           PanelDesc *pd_next, SolverState *st, long long *hist_r, u64 *hist_pm, u64 colmask_next,
+           const DistLook *dl = nullptr) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint4 *TD = reinterpret_cast<uint4 *>(smem_raw);
 #if SW == 16
@@ -782,7 +794,8 @@ sweep_body(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_c
 	const long long units = (long long)(M.ns - s0) * nchunks;
 	/* unit 0 = (strip holding word w+1, first SWEEP_RU active rows) carries the fused
 	 * pivot search: its CTA gets SWEEP_SEL_PAD fewer units */
-	const long long vpad = pd_next ? max(0LL, min((long long)SWEEP_SEL_PAD, units / gridDim.x - 1)) : 0;
+	/* (sharded systems: the search CTA also waits for the peers' candidates and runs the election) */
+	const long long vpad = pd_next ? max(0LL, min((long long)(dl ? dist_sel_pad(dl) : SWEEP_SEL_PAD), units / gridDim.x - 1)) : 0;
 	const long long vunits = units + vpad;
 	const long long u0 = max(0LL, vunits * blockIdx.x / gridDim.x - vpad);
 	const long long u1 = vunits * (blockIdx.x + 1) / gridDim.x - vpad;
@@ -936,7 +949,11 @@ sweep_body(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_c
 			__syncthreads();
 			const long long lim = min(m, r1 + (long long)SWEEP_RU);
 			select_scan(S, pc_next, r1, lim, colmask_next);
-			if (tid < 32) {
+			if (dl) {
+				/* row-sharded system: this shard's candidates go to every peer now, and (one
+				 * process per GPU) the global election runs here too, while the sweep goes on */
+				dist_lookahead(dl, S, pc_next, wn, colmask_next, r1, lim, m, st, pd_next, hist_r, hist_pm);
+			} else if (tid < 32) {
 				if (S.pm == colmask_next || lim == m)
 					select_finalize(S, pc_next, wn, r1, st, pd_next, hist_r, hist_pm);
 				else if (tid == 0)

@@ -97,6 +97,9 @@ __device__ __forceinline__ void hdr_publish(GridSync *gs, int w, long long r1, u
  * append every row whose new panel word is non-zero to a candidate list (warp-aggregated
  * atomics); CTA 0 then scans that list (a few % of the rows on MT19937-class systems)
  * instead of the whole column.  More than PERSIST_CAND_MAX candidates: full scan. */
+#ifndef PERSIST_SEL_PAD
+#define PERSIST_SEL_PAD 14
+#endif
 #ifndef PERSIST_CAND_MAX
 #define PERSIST_CAND_MAX 8192
 #endif
@@ -423,7 +426,10 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 		const long long base8 = r1 & ~7LL; /* chunks start on 512-byte boundaries of the strip */
 		const long long nchunks = (m - base8 + SWEEP_RU - 1) / SWEEP_RU;
 		const long long units = (long long)(M.ns - s0) * nchunks;
-		const long long vpad = has_next ? max(0LL, min((long long)SWEEP_SEL_PAD, units / G - 1)) : 0;
+		/* the CTA that owns unit 0 runs the look-ahead search (~17 us with every other warp of its SM
+		 * idle) and restarts without a prefetched tile: it is dealt PERSIST_SEL_PAD fewer units
+		 * (A/B at n = 131072, profiles/r02_ab.md: 6: 609.7, 10: 605.4, 12: 604.6, 14: 604.2, 16: 604.7 ms) */
+		const long long vpad = has_next ? max(0LL, min((long long)PERSIST_SEL_PAD, units / G - 1)) : 0;
 		const long long vunits = units + vpad;
 		const long long u0 = max(0LL, vunits * blockIdx.x / G - vpad);
 		const long long u1 = vunits * (blockIdx.x + 1) / G - vpad;

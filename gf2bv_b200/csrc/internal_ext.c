@@ -57,10 +57,47 @@ typedef struct {
 } shim_t;
 
 static shim_t g_shim;
-static gf2b200_ctx *g_ctx;
-static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER; /* guards g_ctx, g_stage */
-static uint64_t *g_stage;                                  /* pinned staging, grow-only */
-static size_t g_stage_bytes;
+/* The reference's m4ri_solve can run concurrently from several Python threads (the GIL is
+ * released around M4RI, _internal.c:429).  Here every concurrent call takes its own solver
+ * slot -- a context (stream, HBM buffers of the last shape) plus a pinned staging buffer --
+ * out of a small pool; the lock only guards the pool bookkeeping, never a solve. */
+#define MAX_SLOTS 4
+typedef struct {
+	gf2b200_ctx *ctx;
+	uint64_t *stage; /* pinned staging, grow-only */
+	size_t stage_bytes;
+	int busy;
+} slot_t;
+static slot_t g_slots[MAX_SLOTS];
+static int g_one_slot; /* the kernel tests' CPU emulation build is loaded: never two solves at once */
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER; /* guards g_slots[].busy and shim_load */
+static pthread_cond_t g_cv = PTHREAD_COND_INITIALIZER;
+
+/* GIL released.  Prefers a slot that already has a context. */
+static slot_t *slot_acquire(void) {
+	pthread_mutex_lock(&g_lock);
+	for (;;) {
+		slot_t *pick = NULL;
+		const int nslots = g_one_slot ? 1 : MAX_SLOTS;
+		for (int i = 0; i < nslots; i++)
+			if (!g_slots[i].busy && g_slots[i].ctx) { pick = &g_slots[i]; break; }
+		for (int i = 0; !pick && i < nslots; i++)
+			if (!g_slots[i].busy) pick = &g_slots[i];
+		if (pick) {
+			pick->busy = 1;
+			pthread_mutex_unlock(&g_lock);
+			return pick;
+		}
+		pthread_cond_wait(&g_cv, &g_lock);
+	}
+}
+
+static void slot_release(slot_t *sl) {
+	pthread_mutex_lock(&g_lock);
+	sl->busy = 0;
+	pthread_cond_signal(&g_cv);
+	pthread_mutex_unlock(&g_lock);
+}
 
 static int shim_load(void) {
 	if (g_shim.handle) return 0;
@@ -97,6 +134,7 @@ static int shim_load(void) {
 			dlclose(h);
 			return -1;
 		}
+		g_one_slot = 1; /* the emulator is one OS thread by design: one solve at a time */
 	}
 	shim_t s;
 	memset(&s, 0, sizeof s);
@@ -129,25 +167,24 @@ static int shim_load(void) {
 	return 0;
 }
 
-/* with g_lock held and the GIL held */
-static int ctx_ready(void) {
-	if (g_ctx) return 0;
-	if (shim_load()) return -1;
+/* slot owned, GIL held */
+static int ctx_ready(slot_t *sl) {
+	if (sl->ctx) return 0;
 	const char *dev = getenv("GF2B200_DEVICE");
-	int rc = g_shim.create(&g_ctx, dev ? atoi(dev) : 0);
+	int rc = g_shim.create(&sl->ctx, dev ? atoi(dev) : 0);
 	if (rc) {
 		PyErr_Format(PyExc_RuntimeError, "gf2b200_create failed (%d): %s", rc, g_shim.last_error(NULL));
-		g_ctx = NULL;
+		sl->ctx = NULL;
 		return -1;
 	}
 	return 0;
 }
 
-static uint64_t *stage_reserve(size_t bytes) {
-	if (bytes <= g_stage_bytes) return g_stage;
-	if (g_stage) g_shim.host_free(g_stage);
-	g_stage = NULL;
-	g_stage_bytes = 0;
+static uint64_t *stage_reserve(slot_t *sl, size_t bytes) {
+	if (bytes <= sl->stage_bytes) return sl->stage;
+	if (sl->stage) g_shim.host_free(sl->stage);
+	sl->stage = NULL;
+	sl->stage_bytes = 0;
 	void *p = NULL;
 	size_t want = bytes + bytes / 8 + 4096;
 	if (g_shim.host_alloc(&p, want) != 0 || !p) {
@@ -155,9 +192,9 @@ static uint64_t *stage_reserve(size_t bytes) {
 		             g_shim.last_error(NULL));
 		return NULL;
 	}
-	g_stage = (uint64_t *)p;
-	g_stage_bytes = want;
-	return g_stage;
+	sl->stage = (uint64_t *)p;
+	sl->stage_bytes = want;
+	return sl->stage;
 }
 
 /* ------------------------------------------------------------------------
@@ -568,15 +605,20 @@ static PyObject *m4ri_solve(PyObject *self, PyObject *const *args, Py_ssize_t na
 	const int64_t nw = ((int64_t)cols + 63) / 64;
 	const int64_t bw = ((int64_t)rows + 63) / 64;
 
-	/* another thread may be inside a solve with the GIL released: wait for the
-	 * solver lock without holding the GIL */
-	Py_BEGIN_ALLOW_THREADS
+	/* other threads may be inside solves with the GIL released: take a free solver slot
+	 * (waiting, if all MAX_SLOTS are busy, without holding the GIL) */
 	pthread_mutex_lock(&g_lock);
+	const int lrc = shim_load(); /* GIL held: errors become Python exceptions */
+	pthread_mutex_unlock(&g_lock);
+	if (lrc) return NULL;
+	slot_t *sl;
+	Py_BEGIN_ALLOW_THREADS
+	sl = slot_acquire();
 	Py_END_ALLOW_THREADS
 
 	PyObject *ret = NULL;
-	if (ctx_ready()) goto out;
-	uint64_t *A = stage_reserve(((size_t)rows * nw + bw) * 8);
+	if (ctx_ready(sl)) goto out;
+	uint64_t *A = stage_reserve(sl, ((size_t)rows * nw + bw) * 8);
 	if (!A) goto out;
 	uint64_t *b = A + (size_t)rows * nw; /* the packer writes every word of A and b itself */
 	const int any_b = pack_all(eqs, rows, A, b, nw, cols);
@@ -585,10 +627,10 @@ static PyObject *m4ri_solve(PyObject *self, PyObject *const *args, Py_ssize_t na
 	gf2b200_result res;
 	int rc;
 	Py_BEGIN_ALLOW_THREADS /* reference releases the GIL around M4RI too (:429) */
-	rc = g_shim.solve(g_ctx, A, any_b ? b : NULL, rows, cols, nw, (int)mode, &res);
+	rc = g_shim.solve(sl->ctx, A, any_b ? b : NULL, rows, cols, nw, (int)mode, &res);
 	Py_END_ALLOW_THREADS
 	if (rc) {
-		PyErr_Format(PyExc_RuntimeError, "gf2b200_solve failed (%d): %s", rc, g_shim.last_error(g_ctx));
+		PyErr_Format(PyExc_RuntimeError, "gf2b200_solve failed (%d): %s", rc, g_shim.last_error(sl->ctx));
 		goto out;
 	}
 	if (res.status == GF2B200_INCONSISTENT) {
@@ -618,7 +660,7 @@ static PyObject *m4ri_solve(PyObject *self, PyObject *const *args, Py_ssize_t na
 		ret = space_new(cols, dim, origin, basis);
 	}
 out:
-	pthread_mutex_unlock(&g_lock);
+	slot_release(sl);
 	return ret;
 }
 
