@@ -52,8 +52,12 @@ struct GridSync {
 	uint4 hdr[2];
 };
 
-__device__ __forceinline__ void hdr_publish(GridSync *gs, int w, long long r1, u64 pm) {
-	__stcg(&gs->hdr[w & 1], make_uint4((unsigned)(w + 1), (unsigned)r1, (unsigned)pm, (unsigned)(pm >> 32)));
+/* bit 31 of the first word: "the rows selected for this panel all came from its first 1024 active
+ * rows" -- the look-ahead of the next panel is worth trying (set by the look-ahead itself, and by the
+ * slow path when a dense-looking panel follows a sparse one) */
+__device__ __forceinline__ void hdr_publish(GridSync *gs, int w, long long r1, u64 pm, bool window_ok) {
+	__stcg(&gs->hdr[w & 1], make_uint4((unsigned)(w + 1) | (window_ok ? 0x80000000u : 0u), (unsigned)r1, (unsigned)pm,
+	                                   (unsigned)(pm >> 32)));
 }
 
 /* How the sweep reads a row's coefficient (the panel word pc_cur[row]):
@@ -355,7 +359,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 
 		/* ---- slow path: nobody settled this panel ahead of time ---------------- */
 		uint4 hd = __ldcg(&gs->hdr[w & 1]);
-		const bool slow = (int)hd.x != w + 1;
+		const bool slow = (int)(hd.x & 0x7fffffffu) != w + 1;
 		if (slow) {
 			u64 colmask = ~0ULL;
 			if (w == nw - 1 && (M.n & 63)) colmask = (1ULL << (M.n & 63)) - 1;
@@ -369,10 +373,15 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 				else
 					select_scan(S, pc_cur, r, m, colmask);
 				if (tid < 32) {
+					/* did every selected row come from the first 1024 active rows?  (S.sel is read before
+					 * select_finalize, which leaves it untouched) */
+					int far = 0;
+					for (int l = tid; l < S.nsel; l += 32) far |= (S.sel[l] >= (r & ~7LL) + SWEEP_RU);
+					const bool window_ok = !__any_sync(0xffffffffu, far);
 					select_finalize(S, pc_cur, w, r, st, pd, hist_r, hist_pm);
 					__syncwarp();
 					if (tid == 0) {
-						hdr_publish(gs, w, r + S.nsel, S.pm);
+						hdr_publish(gs, w, r + S.nsel, S.pm, window_ok);
 						__threadfence();
 						st_release_gpu(&gs->sel_flag, (unsigned)w + 1);
 					}
@@ -398,6 +407,11 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 		/* collect candidates for the next panel while sweeping a panel that needed the slow path */
 		const bool collect = slow;
 		list_ready = false;
+		/* sparse / rank-deficient mode: a panel whose pivots did NOT all come from its first 1024 rows
+		 * is followed by one that most likely needs all rows too -- the look-ahead search (17 us of one
+		 * CTA, and everybody's wait for its verdict) is skipped and the panel goes straight to the
+		 * candidate list.  A panel settled from its first rows switches the look-ahead back on. */
+		const bool try_window = (hd.x >> 31) != 0;
 
 		const long long r1 = (long long)hd.y;
 		const u64 pm = ((u64)hd.w << 32) | hd.z;
@@ -429,7 +443,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 		/* the CTA that owns unit 0 runs the look-ahead search (~17 us with every other warp of its SM
 		 * idle) and restarts without a prefetched tile: it is dealt PERSIST_SEL_PAD fewer units
 		 * (A/B at n = 131072, profiles/r02_ab.md: 6: 609.7, 10: 605.4, 12: 604.6, 14: 604.2, 16: 604.7 ms) */
-		const long long vpad = has_next ? max(0LL, min((long long)PERSIST_SEL_PAD, units / G - 1)) : 0;
+		const long long vpad = (has_next && try_window) ? max(0LL, min((long long)PERSIST_SEL_PAD, units / G - 1)) : 0;
 		const long long vunits = units + vpad;
 		const long long u0 = max(0LL, vunits * blockIdx.x / G - vpad);
 		const long long u1 = vunits * (blockIdx.x + 1) / G - vpad;
@@ -506,7 +520,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 #pragma unroll
 				for (int q = 0; q < SWEEP_U; q++) {
 					if (!act[q]) {
-						if (has_next && u == 0 && ch == nch) S.qv[rl + (SWEEP_THREADS / SQ) * q] = 0;
+						if (has_next && try_window && u == 0 && ch == nch) S.qv[rl + (SWEEP_THREADS / SQ) * q] = 0;
 						continue;
 					}
 					uint4 v = d[q];
@@ -527,7 +541,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 						const long long row = row0 + (SWEEP_THREADS / SQ) * q;
 						const u64 nv = (wn & 1) ? (((u64)v.w << 32) | v.z) : (((u64)v.y << 32) | v.x);
 						__stcg(pc_next + row, nv);
-						if (has_next && u == 0) S.qv[rl + (SWEEP_THREADS / SQ) * q] = nv; /* for the look-ahead search */
+						if (has_next && try_window && u == 0) S.qv[rl + (SWEEP_THREADS / SQ) * q] = nv; /* for the look-ahead search */
 					}
 				}
 				if (force && collect && has_next) {
@@ -553,7 +567,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 						}
 					}
 				}
-				if (has_next && u == 0) {
+				if (has_next && try_window && u == 0) {
 					/* look-ahead: this CTA just produced word w+1 of the first active rows; search
 					 * them for the next panel's pivots while the other SMs keep streaming */
 					__threadfence_block();
@@ -568,7 +582,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 						__syncwarp();
 						TRACE_W0(0); /* (slot 0 re-used by the search CTA: finalize done) */
 						if (tid == 0) {
-							if (final_) hdr_publish(gs, wn, r1 + S.nsel, S.pm);
+							if (final_) hdr_publish(gs, wn, r1 + S.nsel, S.pm, true);
 							__threadfence();
 							st_release_gpu(final_ ? &gs->sel_flag : &gs->need_full, (unsigned)wn + 1);
 						}
@@ -585,9 +599,12 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 		if (has_next) {
 			__syncthreads(); /* the tables are dead: their space is the apply scratch */
 			if (tid == 0) {
-				int state = 0;
-				if (persist_wait(&gs->sel_flag, (unsigned)wn + 1, &gs->need_full, gs))
-					state = ((int)(ld_acquire_gpu(&gs->sel_flag) - ((unsigned)wn + 1)) >= 0) ? 1 : 2;
+				int state = 2; /* no look-ahead ran: the next panel takes the slow path */
+				if (try_window) {
+					state = 0;
+					if (persist_wait(&gs->sel_flag, (unsigned)wn + 1, &gs->need_full, gs))
+						state = ((int)(ld_acquire_gpu(&gs->sel_flag) - ((unsigned)wn + 1)) >= 0) ? 1 : 2;
+				}
 				__threadfence();
 				*s_state = state;
 			}

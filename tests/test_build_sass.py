@@ -48,10 +48,11 @@ def test_built_for_sm_100a_only(lib):
 def test_resource_usage(lib):
     txt = subprocess.run([CUOBJDUMP, "-res-usage", str(lib)], capture_output=True, text=True).stdout
     usage = _functions(txt, r"Function (\S+):")
-    sweep = [v for k, v in usage.items() if "k_sweep" in k]
-    assert len(sweep) == 1
-    regs = int(re.search(r"REG:(\d+)", sweep[0]).group(1))
-    assert regs <= 64, "k_sweep must fit 1024 threads x 64 registers on one SM"
+    sweep = [v for k, v in usage.items() if "k_sweepE" in k or "k_sweep_distE" in k]
+    assert len(sweep) == 2, "k_sweep and its sharded variant k_sweep_dist"
+    for body in sweep:
+        regs = int(re.search(r"REG:(\d+)", body).group(1))
+        assert regs <= 64, "the sweep kernels must fit 1024 threads x 64 registers on one SM"
     fwd = [v for k, v in usage.items() if "k_forward" in k]
     assert len(fwd) == 1 and int(re.search(r"REG:(\d+)", fwd[0]).group(1)) <= 64
     for name, body in usage.items():
@@ -67,7 +68,7 @@ def test_resource_usage(lib):
 def test_sweep_sass_shape(lib):
     txt = subprocess.run([CUOBJDUMP, "-sass", str(lib)], capture_output=True, text=True).stdout
     fn = _functions(txt, r"Function : (\S+)")
-    sweep = next(v for k, v in fn.items() if "k_sweep" in k)
+    sweep = next(v for k, v in fn.items() if "k_sweepE" in k)
     assert "UBLKCP" in sweep, "the pivot-row tile is staged by a bulk async copy (TMA)"
     assert "SYNCS.PHASECHK" in sweep and "SYNCS.ARRIVE.TRANS64" in sweep, "mbarrier wait / expect_tx"
     assert sweep.count("LDG.E.128") == 4 and sweep.count("STG.E.128") == 4, "four row pieces in flight, 128-bit"
