@@ -26,6 +26,8 @@ EXPORTS = [
     "gf2b200_system_load_device", "gf2b200_system_generate", "gf2b200_system_eliminate",
     "gf2b200_system_result", "gf2b200_system_stats", "gf2b200_system_check_synthetic",
     "gf2b200_host_alloc", "gf2b200_host_free", "gf2b200_create_shards", "gf2b200_synth_host",
+    "gf2b200_system_load_begin", "gf2b200_system_load_rows", "gf2b200_system_load_end",
+    "gf2b200_solve_open", "gf2b200_solve_close",
 ]
 
 
@@ -116,6 +118,11 @@ def lib() -> ctypes.CDLL:
     L.gf2b200_system_local_rows.restype = i64
     L.gf2b200_system_load_host.argtypes = [vp, u64p, u64p, i64]
     L.gf2b200_system_load_device.argtypes = [vp, u64p, u64p, i64]
+    L.gf2b200_system_load_begin.argtypes = [vp, i64]
+    L.gf2b200_system_load_rows.argtypes = [vp, u64p, i64, i64]
+    L.gf2b200_system_load_end.argtypes = [vp, u64p]
+    L.gf2b200_solve_open.argtypes = [vp, i64, i64, ctypes.POINTER(vp)]
+    L.gf2b200_solve_close.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(CResult)]
     L.gf2b200_system_generate.argtypes = [vp, ctypes.c_uint64]
     L.gf2b200_system_eliminate.argtypes = [vp]
     L.gf2b200_system_result.argtypes = [vp, ctypes.c_int, ctypes.POINTER(CResult)]
@@ -242,6 +249,20 @@ class System:
             b = np.ascontiguousarray(b, dtype=np.uint64)
             bp = b.ctypes.data
         self.ctx._check(lib().gf2b200_system_load_host(self._h, A.ctypes.data, bp, A.shape[1]), "load_host")
+
+    def load_host_blocks(self, A: np.ndarray, b: Optional[np.ndarray], order):
+        """the streaming form of load_host (gf2b200_system_load_begin / _rows / _end): `order` lists
+        (row0, nrows) blocks of the local rows, handed over in that order"""
+        A = np.ascontiguousarray(A, dtype=np.uint64)
+        bp = None
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=np.uint64)
+            bp = b.ctypes.data
+        L = lib()
+        self.ctx._check(L.gf2b200_system_load_begin(self._h, A.shape[1]), "load_begin")
+        for row0, nrows in order:
+            self.ctx._check(L.gf2b200_system_load_rows(self._h, A[row0:].ctypes.data, row0, nrows), "load_rows")
+        self.ctx._check(L.gf2b200_system_load_end(self._h, bp), "load_end")
 
     def load_host_ptr(self, A_ptr: int, b_ptr: Optional[int], stride: int):
         self.ctx._check(lib().gf2b200_system_load_host(self._h, A_ptr, b_ptr, stride), "load_host")

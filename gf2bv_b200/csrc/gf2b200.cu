@@ -94,6 +94,8 @@ struct Shard {
 	u64 *d_slab; /* BS_S*64 rows x BS_W */
 	u64 *d_slab_all;
 	std::vector<long long> hist_r;
+	/* kernel basis on a sharded system (alive only inside system_result) */
+	void *bk_send, *bk_recv;
 };
 
 struct gf2b200_system {
@@ -106,6 +108,9 @@ struct gf2b200_system {
 	int inconsistent;
 	int eliminated;
 	unsigned epoch_base; /* flag epochs of the peer-memory exchange only ever grow */
+	/* a host-buffer load in progress (system_load_begin .. system_load_end) */
+	long long ld_stride, ld_chunk_rows;
+	int ld_ci, ld_used[2];
 	gf2b200_stats stats;
 	std::vector<cudaEvent_t> ev;
 };
@@ -551,34 +556,45 @@ extern "C" int gf2b200_system_load_device(gf2b200_system *sys, const uint64_t *d
 	return GF2B200_OK;
 }
 
-extern "C" int gf2b200_system_load_host(gf2b200_system *sys, const uint64_t *A, const uint64_t *b,
-                                        int64_t stride64) {
-	if (!sys || !A) return fail(sys ? sys->ctx : nullptr, GF2B200_EINVAL, "NULL argument");
+/* ---- host-buffer loads -------------------------------------------------------------
+ * Rows travel in chunks through two device staging buffers: the copy of chunk c+1 (copy
+ * stream) overlaps the layout kernel of chunk c (solver stream).  Buffers, stream and
+ * events belong to the context and are reused by every load.  The load is split in
+ * begin / rows / end so that a caller who is still PRODUCING rows (the extension packing
+ * PyLongs on worker threads) can hand finished blocks over one by one: H2D and layout of a
+ * block overlap the packing of the next (the reference packs everything, then calls
+ * M4RI: _internal.c:403-426 followed by :433). */
+static int load_error(gf2b200_system *sys, cudaError_t e, const char *where) {
+	gf2b200_ctx *ctx = sys->ctx;
+	const int rc = fail(ctx, GF2B200_ECUDA, "%s: %s", where, cudaGetErrorString(e));
+	if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+	cudaStreamSynchronize(ctx->stream);
+	sys->ld_stride = 0;
+	return rc;
+}
+
+extern "C" int gf2b200_system_load_begin(gf2b200_system *sys, int64_t stride64) {
+	if (!sys) return fail(nullptr, GF2B200_EINVAL, "NULL argument");
 	gf2b200_ctx *ctx = sys->ctx;
 	if (stride64 < sys->sh[0].M.nw) return fail(ctx, GF2B200_EINVAL, "stride64 < ceil(n/64)");
 	CK(ctx, cudaSetDevice(ctx->device));
 	const long long m_loc = gf2b200_system_local_rows(sys);
-	const long long base = sys->sh[0].row_begin;
-	/* rows travel in chunks through two device staging buffers: the copy of chunk
-	 * c+1 (copy stream) overlaps the layout kernel of chunk c (solver stream).  Buffers,
-	 * stream and events belong to the context and are reused by every load. */
 	const size_t row_bytes = (size_t)stride64 * 8;
 	long long chunk_rows = std::max<long long>(1, (long long)((64u << 20) / row_bytes));
 	chunk_rows = std::min<long long>(chunk_rows, std::max<long long>(m_loc, 1));
 	const size_t need = (size_t)chunk_rows * row_bytes;
-	const bool two = chunk_rows < m_loc;
 	cudaError_t e = cudaSuccess;
-	if (ctx->stage_bytes < need || (two && !ctx->stage[1])) {
+	if (ctx->stage_bytes < need || !ctx->stage[1]) {
 		cudaFree(ctx->stage[0]);
 		cudaFree(ctx->stage[1]);
 		ctx->stage[0] = ctx->stage[1] = nullptr;
 		ctx->stage_bytes = 0;
 		e = cudaMalloc(&ctx->stage[0], need);
-		if (e == cudaSuccess && two) e = cudaMalloc(&ctx->stage[1], need);
+		if (e == cudaSuccess) e = cudaMalloc(&ctx->stage[1], need);
 		if (e == cudaSuccess) ctx->stage_bytes = need;
 	}
 	const size_t b_bytes = (size_t)((m_loc + 63) / 64) * 8;
-	if (e == cudaSuccess && b && ctx->bstage_bytes < b_bytes) {
+	if (e == cudaSuccess && ctx->bstage_bytes < b_bytes) {
 		cudaFree(ctx->d_bstage);
 		ctx->d_bstage = nullptr;
 		ctx->bstage_bytes = 0;
@@ -592,50 +608,91 @@ extern "C" int gf2b200_system_load_host(gf2b200_system *sys, const uint64_t *A, 
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_laid[i], cudaEventDisableTiming);
 		}
 	}
-	u64 **stage = ctx->stage;
-	u64 *d_b = b ? ctx->d_bstage : nullptr;
-	cudaStream_t copy_stream = ctx->copy_stream;
-	cudaEvent_t *copied = ctx->ev_copied, *laid = ctx->ev_laid;
-	int rc = GF2B200_OK;
 	/* the previous load's last layout kernels may still be reading the staging buffers */
-	if (e == cudaSuccess) e = cudaEventRecord(laid[0], ctx->stream);
-	if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, laid[0], 0);
-	if (e == cudaSuccess && b)
-		e = cudaMemcpyAsync(d_b, b, b_bytes, cudaMemcpyHostToDevice, ctx->stream);
-	int ci = 0, used[2] = {0, 0};
+	if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_laid[0], ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_laid[0], 0);
+	if (e != cudaSuccess) return load_error(sys, e, "system_load_begin");
+	sys->ld_stride = stride64;
+	sys->ld_chunk_rows = chunk_rows;
+	sys->ld_ci = 0;
+	sys->ld_used[0] = sys->ld_used[1] = 0;
+	sys->eliminated = 0;
+	return GF2B200_OK;
+}
+
+/* rows [row0, row0 + nrows) of this rank's rows; A_rows points at row row0.  The host memory
+ * must stay valid until gf2b200_system_load_end returns.  Any order, no overlaps. */
+extern "C" int gf2b200_system_load_rows(gf2b200_system *sys, const uint64_t *A_rows, int64_t row0, int64_t nrows) {
+	if (!sys || !A_rows) return fail(sys ? sys->ctx : nullptr, GF2B200_EINVAL, "NULL argument");
+	gf2b200_ctx *ctx = sys->ctx;
+	if (!sys->ld_stride) return fail(ctx, GF2B200_EINVAL, "system_load_rows without system_load_begin");
+	if (row0 < 0 || nrows < 0 || row0 + nrows > gf2b200_system_local_rows(sys))
+		return fail(ctx, GF2B200_EINVAL, "system_load_rows: rows out of range");
+	CK(ctx, cudaSetDevice(ctx->device));
+	const long long stride64 = sys->ld_stride, chunk_rows = sys->ld_chunk_rows;
+	const size_t row_bytes = (size_t)stride64 * 8;
+	const long long base = sys->sh[0].row_begin;
+	cudaError_t e = cudaSuccess;
 	for (Shard &h : sys->sh) {
+		/* the part of the block that falls into this shard (loopback contexts hold several) */
 		const long long off = h.row_begin - base;
-		for (long long row0 = 0; e == cudaSuccess && row0 < h.M.m; row0 += chunk_rows) {
-			long long nr = std::min<long long>(chunk_rows, h.M.m - row0);
-			const int bi = stage[1] ? ci : 0;
+		const long long lo = std::max<long long>(row0, off), hi = std::min<long long>(row0 + nrows, off + h.M.m);
+		for (long long r = lo; e == cudaSuccess && r < hi; r += chunk_rows) {
+			const long long nr = std::min<long long>(chunk_rows, hi - r);
+			const int bi = sys->ld_ci;
 			/* the staging buffer is free once the layout kernel that read it is done */
-			if (used[bi]) e = cudaStreamWaitEvent(copy_stream, laid[bi], 0);
+			if (sys->ld_used[bi]) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_laid[bi], 0);
 			if (e == cudaSuccess)
-				e = cudaMemcpyAsync(stage[bi], A + (off + row0) * stride64, nr * row_bytes,
-				                    cudaMemcpyHostToDevice, copy_stream);
-			if (e == cudaSuccess) e = cudaEventRecord(copied[bi], copy_stream);
-			if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, copied[bi], 0);
+				e = cudaMemcpyAsync(ctx->stage[bi], A_rows + (r - row0) * stride64, nr * row_bytes,
+				                    cudaMemcpyHostToDevice, ctx->copy_stream);
+			if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copied[bi], ctx->copy_stream);
+			if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[bi], 0);
 			if (e != cudaSuccess) break;
-			long long total = nr * h.M.ns * SW;
-			k_layout<<<grid_for(total, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
-			    h.M, stage[bi], d_b, stride64, row0, nr, off + row0);
+			const long long total = nr * h.M.ns * SW;
+			k_layout<<<grid_for(total, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(h.M, ctx->stage[bi], nullptr, stride64,
+			                                                                      r - off, nr, 0);
 			e = cudaGetLastError();
-			if (e == cudaSuccess) e = cudaEventRecord(laid[bi], ctx->stream);
-			used[bi] = 1;
-			ci ^= 1;
+			if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_laid[bi], ctx->stream);
+			sys->ld_used[bi] = 1;
+			sys->ld_ci ^= 1;
 		}
 	}
-	/* the caller's host buffers are free again once every copy has left them; the layout
-	 * kernels still in flight are ordered before whatever the caller enqueues next on the
-	 * solver stream (gf2b200_system_eliminate) */
-	if (e == cudaSuccess) e = cudaStreamSynchronize(copy_stream);
-	if (e == cudaSuccess && b) e = cudaStreamSynchronize(ctx->stream); /* b travels on the solver stream */
-	if (e != cudaSuccess) {
-		rc = fail(ctx, GF2B200_ECUDA, "system_load_host: %s", cudaGetErrorString(e));
-		cudaStreamSynchronize(copy_stream);
-		cudaStreamSynchronize(ctx->stream);
+	if (e != cudaSuccess) return load_error(sys, e, "system_load_rows");
+	return GF2B200_OK;
+}
+
+/* b: the packed bits of the local rows (NULL: homogeneous).  Returns when every copy has left
+ * the caller's host buffers; the layout kernels still in flight are ordered before whatever the
+ * caller enqueues next on the solver stream (gf2b200_system_eliminate). */
+extern "C" int gf2b200_system_load_end(gf2b200_system *sys, const uint64_t *b) {
+	if (!sys) return fail(nullptr, GF2B200_EINVAL, "NULL argument");
+	gf2b200_ctx *ctx = sys->ctx;
+	if (!sys->ld_stride) return fail(ctx, GF2B200_EINVAL, "system_load_end without system_load_begin");
+	CK(ctx, cudaSetDevice(ctx->device));
+	cudaError_t e = cudaSuccess;
+	if (b) {
+		const long long m_loc = gf2b200_system_local_rows(sys);
+		const long long base = sys->sh[0].row_begin;
+		e = cudaMemcpyAsync(ctx->d_bstage, b, (size_t)((m_loc + 63) / 64) * 8, cudaMemcpyHostToDevice, ctx->stream);
+		for (Shard &h : sys->sh) {
+			if (e != cudaSuccess || h.M.m == 0) continue;
+			k_place_b<<<grid_for(h.M.m, 256, ctx->n_sm * 8), 256, 0, ctx->stream>>>(h.M, ctx->d_bstage, h.row_begin - base);
+			e = cudaGetLastError();
+		}
 	}
-	sys->eliminated = 0;
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
+	if (e == cudaSuccess && b) e = cudaStreamSynchronize(ctx->stream); /* b travels on the solver stream */
+	if (e != cudaSuccess) return load_error(sys, e, "system_load_end");
+	sys->ld_stride = 0;
+	return GF2B200_OK;
+}
+
+extern "C" int gf2b200_system_load_host(gf2b200_system *sys, const uint64_t *A, const uint64_t *b,
+                                        int64_t stride64) {
+	if (!sys || !A) return fail(sys ? sys->ctx : nullptr, GF2B200_EINVAL, "NULL argument");
+	int rc = gf2b200_system_load_begin(sys, stride64);
+	if (!rc) rc = gf2b200_system_load_rows(sys, A, 0, gf2b200_system_local_rows(sys));
+	if (!rc) rc = gf2b200_system_load_end(sys, b);
 	return rc;
 }
 
@@ -1031,6 +1088,140 @@ extern "C" int gf2b200_system_stats(const gf2b200_system *sys, gf2b200_stats *ou
 	return GF2B200_OK;
 }
 
+/* Kernel basis of a row-sharded system: the blocked multi-right-hand-side triangular solve of
+ * gf2b200_basis.cuh with F split by rows like the matrix (every shard holds F for its own echelon
+ * rows) and ONE small exchange per backward panel.  Every rank of an NCCL context calls this
+ * together and gets the whole basis.  Replaces mzd_trsm_upper_left (_internal.c:343). */
+struct BasisShard {
+	Mat F;
+	long long r_loc;
+	long long *d_free;
+	u64 *d_pc, *d_part, *d_all;
+	uint4 *d_ebuf, *d_tile, *d_tiles_all;
+	PanelDesc *d_pd;
+};
+
+static int basis_sharded(gf2b200_system *sys, const std::vector<long long> &sigma, long long r, long long d,
+                         uint64_t *basis_out) {
+	gf2b200_ctx *ctx = sys->ctx;
+	const int nw = sys->sh[0].M.nw;
+	const int G = ctx->world;
+	const size_t L = sys->sh.size();
+	std::vector<BasisShard> bs(L);
+	cudaError_t e = cudaSuccess;
+	int rc = GF2B200_OK;
+	const int fnw = (int)((d + 63) / 64), fns = (fnw + SW - 1) / SW;
+	const size_t tile_bytes = (size_t)fns * EBUF_Q * 16;
+	/* batches bound the exchange buffers for huge nullities */
+	const long long batch = std::min<long long>(d, std::max<long long>(1, (1LL << 28) / ((long long)nw * 8 * G)));
+	for (size_t l = 0; l < L; l++) {
+		Shard &h = sys->sh[l];
+		BasisShard &b = bs[l];
+		memset(&b, 0, sizeof b);
+		for (int w = 0; w < nw; w++) {
+			const int k = __builtin_popcountll(sys->hist_pm[w]);
+			for (int j = 0; j < k; j++) b.r_loc += sys->hist_owner[(size_t)w * 64 + j] == h.index;
+		}
+		b.F.m = b.r_loc;
+		b.F.n = d;
+		b.F.nw = fnw;
+		b.F.ns = fns;
+		b.F.mp = (std::max<long long>(b.r_loc, 1) + 15) / 16 * 16;
+		if (e == cudaSuccess) e = cudaMalloc(&b.d_free, (size_t)d * 8);
+		if (e == cudaSuccess) e = cudaMalloc(&b.F.base, (size_t)fns * (size_t)b.F.mp * SBYTES);
+		if (e == cudaSuccess) e = cudaMalloc(&b.d_pc, (size_t)b.F.mp * 8);
+		if (e == cudaSuccess) e = cudaMalloc(&b.d_ebuf, tile_bytes);
+		if (e == cudaSuccess) e = cudaMalloc(&b.d_tile, tile_bytes);
+		if (e == cudaSuccess) e = cudaMalloc(&b.d_tiles_all, tile_bytes * G);
+		if (e == cudaSuccess) e = cudaMalloc(&b.d_pd, sizeof(PanelDesc));
+		if (e == cudaSuccess) e = cudaMalloc(&b.d_part, (size_t)batch * nw * 8);
+		if (e == cudaSuccess) e = cudaMalloc(&b.d_all, (size_t)batch * nw * 8 * G);
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(b.d_free, sigma.data() + r, (size_t)d * 8, cudaMemcpyHostToDevice, ctx->stream);
+		if (e == cudaSuccess && b.r_loc > 0)
+			k_basis_gather<<<grid_for(b.r_loc * fns * SW, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
+			    h.M, b.F, b.d_free, h.d_hist_r, b.r_loc, d);
+	}
+	cudaEvent_t tb0 = sys->ev[3], tb1 = sys->ev[4], tb2 = sys->ev[5];
+	double bk_bytes = 0;
+	long long bk_panels = 0;
+	if (e == cudaSuccess) e = cudaEventRecord(tb0, ctx->stream);
+	for (int w = nw - 1; w >= 0 && e == cudaSuccess && !rc; --w) {
+		const u64 pm = sys->hist_pm[w];
+		if (!pm) continue;
+		for (size_t l = 0; l < L; l++) {
+			Shard &h = sys->sh[l];
+			BasisShard &b = bs[l];
+			k_basis_tile<<<grid_for((long long)fns * EBUF_Q, 256, ctx->n_sm * 4), 256, 0, ctx->stream>>>(
+			    b.F, w, pm, h.hist_r[w], h.d_hist_owner, h.index, b.d_tile);
+			h.bk_send = b.d_tile;
+			h.bk_recv = b.d_tiles_all;
+		}
+		rc = all_gather(sys, &Shard::bk_send, &Shard::bk_recv, tile_bytes, nullptr);
+		for (size_t l = 0; l < L && !rc; l++) {
+			Shard &h = sys->sh[l];
+			BasisShard &b = bs[l];
+			const long long r_w = h.hist_r[w];
+			k_basis_prep_sharded<<<grid_for(std::max<long long>(r_w, (long long)fns * EBUF_Q), 256, ctx->n_sm * 8), 256, 0,
+			                       ctx->stream>>>(h.M, b.F, w, pm, r_w, b.d_pc, b.d_ebuf, b.d_pd, b.d_tiles_all, G);
+			if (r_w <= 0) continue;
+			Mat Fv = b.F;
+			Fv.m = r_w; /* this shard's rows above the panel */
+			k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, ctx->stream>>>(Fv, b.d_pd, b.d_pc, nullptr, b.d_ebuf, 0, 0, nullptr,
+			                                                              nullptr, nullptr, nullptr, 0);
+			bk_bytes += 2.0 * (double)r_w * (double)SBYTES * (double)fns;
+		}
+		bk_panels++;
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess) e = cudaEventRecord(tb1, ctx->stream);
+	for (long long b0 = 0; e == cudaSuccess && !rc && b0 < d; b0 += batch) {
+		const long long nb = std::min(batch, d - b0);
+		for (size_t l = 0; l < L; l++) {
+			Shard &h = sys->sh[l];
+			BasisShard &b = bs[l];
+			k_basis_scatter_sharded<<<grid_for(nb * nw, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(
+			    b.F, h.d_hist_r, h.d_hist_pm, h.d_hist_owner, h.index, b.d_free, nw, b0, nb, b.d_part);
+			h.bk_send = b.d_part;
+			h.bk_recv = b.d_all;
+		}
+		rc = all_gather(sys, &Shard::bk_send, &Shard::bk_recv, (size_t)nb * nw * 8, nullptr);
+		if (rc) break;
+		k_or_parts<<<grid_for(nb * nw, 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(bs[0].d_part, bs[0].d_all, nb * nw, G);
+		e = cudaGetLastError();
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(basis_out + b0 * nw, bs[0].d_part, (size_t)nb * nw * 8, cudaMemcpyDeviceToHost, ctx->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	}
+	if (e == cudaSuccess) e = cudaEventRecord(tb2, ctx->stream);
+	if (e == cudaSuccess) e = cudaEventSynchronize(tb2);
+	else cudaStreamSynchronize(ctx->stream);
+	if (e == cudaSuccess && !rc) {
+		float ms1 = 0, ms2 = 0;
+		cudaEventElapsedTime(&ms1, tb0, tb1);
+		cudaEventElapsedTime(&ms2, tb1, tb2);
+		sys->stats.ms_basis_solve = ms1;
+		sys->stats.ms_basis_output = ms2;
+		sys->stats.basis_sweep_bytes = bk_bytes;
+		sys->stats.basis_panels = bk_panels;
+	}
+	for (BasisShard &b : bs) {
+		cudaFree(b.d_free);
+		cudaFree(b.F.base);
+		cudaFree(b.d_pc);
+		cudaFree(b.d_ebuf);
+		cudaFree(b.d_tile);
+		cudaFree(b.d_tiles_all);
+		cudaFree(b.d_pd);
+		cudaFree(b.d_part);
+		cudaFree(b.d_all);
+	}
+	for (Shard &h : sys->sh) h.bk_send = h.bk_recv = nullptr;
+	if (rc) return rc;
+	if (e != cudaSuccess) return fail(ctx, GF2B200_ECUDA, "kernel basis (sharded): %s", cudaGetErrorString(e));
+	return GF2B200_OK;
+}
+
 extern "C" int gf2b200_system_result(gf2b200_system *sys, int mode, gf2b200_result *out) {
 	if (!sys || !out) return fail(sys ? sys->ctx : nullptr, GF2B200_EINVAL, "NULL argument");
 	gf2b200_ctx *ctx = sys->ctx;
@@ -1079,30 +1270,12 @@ extern "C" int gf2b200_system_result(gf2b200_system *sys, int mode, gf2b200_resu
 			return fail(ctx, GF2B200_ENOMEM, "malloc basis");
 		}
 		if (ctx->world > 1) {
-			/* row-sharded system: one blocked back-substitution per free column over the
-			 * shards' echelon rows (same kernels and slab exchange as the particular
-			 * solution; every rank of an NCCL context calls this together and gets the
-			 * whole basis).  d_x is restored to the particular solution afterwards. */
-			long long launches = 0;
-			double xbytes = 0;
-			int rc = GF2B200_OK;
-			cudaError_t e = cudaSuccess;
-			for (long long i = 0; i < d && !rc && e == cudaSuccess; i++) {
-				rc = backward(sys, &launches, &xbytes, sigma[r + i]);
-				if (!rc)
-					e = cudaMemcpyAsync(out->basis + i * nw, h.d_x, (size_t)nw * 8, cudaMemcpyDeviceToHost,
-					                    ctx->stream);
-			}
-			for (Shard &sh : sys->sh) {
-				static const u64 one = 1;
-				if (e == cudaSuccess)
-					e = cudaMemcpyAsync(sh.d_x, out->origin, (size_t)nw * 8, cudaMemcpyHostToDevice, ctx->stream);
-				if (e == cudaSuccess) e = cudaMemcpyAsync(sh.d_x + nw, &one, 8, cudaMemcpyHostToDevice, ctx->stream);
-			}
-			if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-			if (rc || e != cudaSuccess) {
+			/* row-sharded system: the same blocked solve with F split by rows like the matrix and
+			 * one small exchange per backward panel (basis_sharded above) */
+			const int rc = basis_sharded(sys, sigma, r, d, out->basis);
+			if (rc) {
 				gf2b200_result_free(out);
-				return rc ? rc : fail(ctx, GF2B200_ECUDA, "kernel basis (sharded): %s", cudaGetErrorString(e));
+				return rc;
 			}
 			out->kernel_dim = d;
 			out->status = GF2B200_OK;
@@ -1266,31 +1439,66 @@ extern "C" int gf2b200_synth_host(uint64_t *A, uint64_t *b, int64_t row0, int64_
 }
 
 /* ---- one-shot host-buffer solve (what m4ri_solve's body becomes) ---------- */
-extern "C" int gf2b200_solve(gf2b200_ctx *ctx, const uint64_t *A, const uint64_t *b, int64_t m,
-                             int64_t n, int64_t stride64, int mode, gf2b200_result *out) {
-	if (!ctx || !A || !out) return fail(ctx, GF2B200_EINVAL, "NULL argument");
-	memset(out, 0, sizeof *out);
-	if (mode != 0 && mode != 1) return fail(ctx, GF2B200_EINVAL, "Invalid mode");
+/* Repeated solves of one shape (the common case behind LinearSystem) keep their HBM
+ * buffers: cudaMalloc/cudaFree of the matrix costs as much as its H2D copy.  open hands
+ * out the context's cached system of that shape (or a new one), close solves and puts it
+ * back; between the two the caller loads the rows (system_load_host, or begin/rows/end
+ * while it is still packing them). */
+extern "C" int gf2b200_solve_open(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2b200_system **out) {
+	if (!ctx || !out) return fail(ctx, GF2B200_EINVAL, "NULL argument");
+	*out = nullptr;
 	if (ctx->nccl) return fail(ctx, GF2B200_EINVAL, "gf2b200_solve needs a single-process context");
-	/* repeated solves of one shape (the common case behind LinearSystem) keep their
-	 * HBM buffers: cudaMalloc/cudaFree of the matrix costs as much as its H2D copy */
 	gf2b200_system *sys = ctx->cached;
 	ctx->cached = nullptr;
-	int rc = GF2B200_OK;
 	if (sys && (sys->m_global != m || sys->n != n)) {
 		gf2b200_system_destroy(sys);
 		sys = nullptr;
 	}
-	if (!sys) rc = gf2b200_system_create(ctx, m, n, &sys);
-	if (rc) return rc;
-	rc = gf2b200_system_load_host(sys, A, b, stride64);
-	if (!rc) rc = gf2b200_system_eliminate(sys);
+	if (!sys) {
+		const int rc = gf2b200_system_create(ctx, m, n, &sys);
+		if (rc) return rc;
+	}
+	*out = sys;
+	return GF2B200_OK;
+}
+
+/* mode < 0: give the system up without solving (a load failed). */
+extern "C" int gf2b200_solve_close(gf2b200_ctx *ctx, gf2b200_system *sys, int mode, gf2b200_result *out) {
+	if (!ctx || !sys) return fail(ctx, GF2B200_EINVAL, "NULL argument");
+	if (mode < 0) {
+		gf2b200_system_destroy(sys);
+		return GF2B200_OK;
+	}
+	if (!out || (mode != 0 && mode != 1)) {
+		gf2b200_system_destroy(sys);
+		return fail(ctx, GF2B200_EINVAL, out ? "Invalid mode" : "NULL argument");
+	}
+	memset(out, 0, sizeof *out);
+	int rc = gf2b200_system_eliminate(sys);
 	if (!rc) rc = gf2b200_system_result(sys, mode, out);
 	if (rc) {
 		gf2b200_system_destroy(sys);
 		out->status = rc;
 	} else {
+		if (ctx->cached) gf2b200_system_destroy(ctx->cached);
 		ctx->cached = sys;
 	}
 	return rc;
+}
+
+extern "C" int gf2b200_solve(gf2b200_ctx *ctx, const uint64_t *A, const uint64_t *b, int64_t m,
+                             int64_t n, int64_t stride64, int mode, gf2b200_result *out) {
+	if (!ctx || !A || !out) return fail(ctx, GF2B200_EINVAL, "NULL argument");
+	memset(out, 0, sizeof *out);
+	if (mode != 0 && mode != 1) return fail(ctx, GF2B200_EINVAL, "Invalid mode");
+	gf2b200_system *sys = nullptr;
+	int rc = gf2b200_solve_open(ctx, m, n, &sys);
+	if (rc) return rc;
+	rc = gf2b200_system_load_host(sys, A, b, stride64);
+	if (rc) {
+		gf2b200_system_destroy(sys);
+		out->status = rc;
+		return rc;
+	}
+	return gf2b200_solve_close(ctx, sys, mode, out);
 }

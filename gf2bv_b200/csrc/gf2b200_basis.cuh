@@ -117,4 +117,101 @@ __global__ void k_basis_scatter(Mat F, const long long *__restrict__ hist_r, con
 	}
 }
 
+/* ---- row-sharded systems --------------------------------------------------------------
+ * Every shard keeps F for ITS echelon rows (local rows 0 .. r_local-1, in panel order).  The k
+ * pivot rows of a panel are spread over the shards (hist_owner[w * 64 + j] = owner of the j-th
+ * pivot of panel w); per backward panel each shard contributes the F rows it owns to the tile,
+ * the contributions are all-gathered (peers' HBM / NCCL -- 64 x d / 8 bytes per shard and panel,
+ * where the per-column scheme ran a whole back-substitution with its own exchanges per free
+ * column), and every shard sweeps its own rows above the panel. */
+__device__ __forceinline__ long long owned_before(const unsigned char *__restrict__ hist_owner, int w, int j, int me) {
+	long long c = 0;
+	for (int jj = 0; jj < j; jj++) c += hist_owner[(long long)w * 64 + jj] == me;
+	return c;
+}
+
+/* this shard's contribution to the tile of backward panel w (zero where another shard owns the pivot) */
+__global__ void k_basis_tile(Mat F, int w, u64 pm, long long r_w, const unsigned char *__restrict__ hist_owner, int me,
+                             uint4 *__restrict__ tile) {
+	const uint4 *fb = reinterpret_cast<const uint4 *>(F.base);
+	const long long tiles = (long long)F.ns * EBUF_Q;
+	for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < tiles; t += (long long)gridDim.x * blockDim.x) {
+		const int s = (int)(t / EBUF_Q), q = (int)(t % EBUF_Q);
+		const int c = q / SQ, ch = q % SQ;
+		uint4 v = make_uint4(0, 0, 0, 0);
+		if ((pm >> c) & 1) {
+			const int j = __popcll(pm & ((1ULL << c) - 1));
+			if (hist_owner[(long long)w * 64 + j] == me)
+				v = fb[((long long)s * F.mp + r_w + owned_before(hist_owner, w, j, me)) * SQ + ch];
+		}
+		tile[t] = v;
+	}
+}
+
+/* k_basis_prep for a shard: the tile is the OR of the G gathered contributions */
+__global__ void k_basis_prep_sharded(Mat M, Mat F, int w, u64 pm, long long r_w, u64 *__restrict__ pc,
+                                     uint4 *__restrict__ ebufF, PanelDesc *pd, const uint4 *__restrict__ tiles_all, int G) {
+	const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	const long long gs = (long long)gridDim.x * blockDim.x;
+	if (gt == 0) {
+		pd->k = __popcll(pm);
+		pd->r = 0;
+		pd->r1 = 0;
+		pd->pm = pm;
+		pd->nmove = 0;
+	}
+	for (long long i = gt; i < r_w; i += gs) pc[i] = M.base[widx(M, i, w)];
+	const long long tiles = (long long)F.ns * EBUF_Q;
+	for (long long t = gt; t < tiles; t += gs) {
+		uint4 v = tiles_all[t];
+		for (int g = 1; g < G; g++) {
+			const uint4 o = tiles_all[(long long)g * tiles + t];
+			v.x |= o.x;
+			v.y |= o.y;
+			v.z |= o.z;
+			v.w |= o.w;
+		}
+		ebufF[t] = v;
+	}
+}
+
+/* this shard's part of rows [i0, i0 + cnt) of the basis: the bits at the pivot columns it owns
+ * (shard 0 adds the 1 at the free column itself); the parts are OR-ed after an all-gather */
+__global__ void k_basis_scatter_sharded(Mat F, const long long *__restrict__ hist_r, const u64 *__restrict__ hist_pm,
+                                        const unsigned char *__restrict__ hist_owner, int me,
+                                        const long long *__restrict__ freecols, int nw, long long i0, long long cnt,
+                                        u64 *__restrict__ out) {
+	const long long total = cnt * nw;
+	for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+	     t += (long long)gridDim.x * blockDim.x) {
+		const int wo = (int)(t / cnt);
+		const long long ii = t - (long long)wo * cnt;
+		const long long i = i0 + ii;
+		u64 pm = hist_pm[wo];
+		long long j = hist_r[wo];
+		u64 v = 0;
+		const int fw = (int)(i >> 6), fb = (int)(i & 63);
+		for (int jj = 0; pm; jj++) {
+			const int c = __ffsll((long long)pm) - 1;
+			pm &= pm - 1;
+			if (hist_owner[(long long)wo * 64 + jj] == me) {
+				v |= ((F.base[widx(F, j, fw)] >> fb) & 1ULL) << c;
+				j++;
+			}
+		}
+		const long long f = freecols[i];
+		if (me == 0 && (int)(f >> 6) == wo) v |= 1ULL << (f & 63);
+		out[ii * nw + wo] = v;
+	}
+}
+
+/* dst[t] = OR over the G gathered parts */
+__global__ void k_or_parts(u64 *__restrict__ dst, const u64 *__restrict__ all, long long words, int G) {
+	for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < words; t += (long long)gridDim.x * blockDim.x) {
+		u64 v = all[t];
+		for (int g = 1; g < G; g++) v |= all[(long long)g * words + t];
+		dst[t] = v;
+	}
+}
+
 } /* namespace gf2b200 */

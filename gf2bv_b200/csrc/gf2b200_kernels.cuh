@@ -150,6 +150,15 @@ __global__ void k_layout(Mat M, const u64 *__restrict__ src, const u64 *__restri
 	}
 }
 
+/* right-hand side of a host-buffer load: bit (brow0 + i) of bsrc -> bit 0 of word nw of local row i
+ * (k_layout left that word 0; b arrives last, when the caller has finished producing the rows) */
+__global__ void k_place_b(Mat M, const u64 *__restrict__ bsrc, long long brow0) {
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M.m; i += (long long)gridDim.x * blockDim.x) {
+		const long long bi = brow0 + i;
+		M.base[widx(M, i, M.nw)] = (bsrc[bi >> 6] >> (bi & 63)) & 1;
+	}
+}
+
 /* Synthetic dense system of SURVEY.md 8(d): word(i, w) = mix(seed + PHI*(i*nw + w + 1)),
  * i = GLOBAL row index (grow0 + local). */
 __global__ void k_generate(Mat M, u64 seed, long long grow0) {

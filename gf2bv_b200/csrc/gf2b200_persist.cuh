@@ -47,6 +47,8 @@ struct GridSync {
 	int fault;           /* a wait timed out */
 	int done_w;          /* panels finished (diagnostic) */
 	unsigned cand_cnt[2]; /* candidate rows collected for panel (slot = panel & 1): see PERSIST_CAND_MAX */
+	unsigned list_cnt[2]; /* length of the candidate list the slow path of panel (slot) used, 0 if none */
+	unsigned pad2[2];
 	/* what every CTA needs at the top of a panel, in ONE 16-byte load: {valid = panel + 1,
 	 * r1 = first active row, pm lo, pm hi}; slot = panel & 1 (k = popcount(pm)) */
 	uint4 hdr[2];
@@ -142,18 +144,19 @@ __device__ __forceinline__ unsigned long long gtimer_ns() { return (unsigned lon
 __device__ __forceinline__ void fence_proxy_async() {}
 #endif
 
-/* one thread: wait until *p - target >= 0 (flags only grow) or the other flag does */
-__device__ __forceinline__ bool persist_wait(const unsigned *p, unsigned target, const unsigned *alt, GridSync *gs) {
+/* one thread: wait until *p - target >= 0 (flags only grow) or the other flag does; returns 1 / 2 for
+ * the flag that did (both loads are acquires), 0 after a fault or a time-out */
+__device__ __forceinline__ int persist_wait(const unsigned *p, unsigned target, const unsigned *alt, GridSync *gs) {
 	const unsigned long long t0 = gtimer_ns();
 	unsigned it = 0;
 	for (;;) {
-		if ((int)(ld_acquire_gpu(p) - target) >= 0) return true;
-		if (alt && (int)(ld_acquire_gpu(alt) - target) >= 0) return true;
+		if ((int)(ld_acquire_gpu(p) - target) >= 0) return 1;
+		if (alt && (int)(ld_acquire_gpu(alt) - target) >= 0) return 2;
 		if ((++it & 31) == 0) {
-			if (*(volatile int *)&gs->fault) return false;
+			if (*(volatile int *)&gs->fault) return 0;
 			if (gtimer_ns() - t0 > PERSIST_TIMEOUT_NS) {
 				atomicOr(&gs->fault, 1);
-				return false;
+				return 0;
 			}
 		}
 		__nanosleep(40);
@@ -318,6 +321,150 @@ __device__ __forceinline__ void persist_apply(const Mat &M, const PanelDesc *pdn
 	}
 }
 
+/* ---- the lean streaming unit ---------------------------------------------------------
+ * ncu on the first k_forward (profiles/r02r_forward_ncu.md): besides l1tex (the lookups) and HBM
+ * the ALU pipe is a co-limiter of the streaming loop -- 450 SASS instructions per unit and
+ * thread where the arithmetic needs ~220: row-range predicates, the look-ahead / candidate-list
+ * branches and, per lookup, the generic-to-shared address conversion the compiler re-derives
+ * when registers are short (S2R CgaCtaId + LEA).  Units that lie entirely inside the active rows
+ * of a strip other than the next panel word's -- all but a few hundred of the 32768 units of a
+ * large panel -- take this path instead: no predicates, 32-bit shared-memory addresses computed
+ * once per thread, one byte extract (ALU) + one multiply-add (FMA pipe) per lookup: 275 instructions
+ * per unit, 651 -> 620 ms at n = 131072 on one box (profiles/r02_ab.md, calls S and T).  Measured and
+ * dropped there: the same loop behind a call boundary (221 instructions but 642 ms), all eight loads
+ * of a unit issued before the first lookup (691 ms: ptxas' own schedule, which requests row piece
+ * q + 2 while piece q is looked up, is the better one), a rolling pipeline that requests unit i + 1
+ * piece by piece (731 ms) and a TMA bulk prefetch of the next units into L2 (650 - 670 ms). */
+#ifndef PERSIST_LEAN_UNITS
+#define PERSIST_LEAN_UNITS 1
+#endif
+
+#ifndef GF2_EMU
+typedef unsigned smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(const void *p) { return (smem_addr_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 lds128(smem_addr_t a) {
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+	return v;
+}
+/* a row load the compiler can neither sink below the test of its coefficient nor drop (the row
+ * loads must not wait for the coefficient: two chained L2 latencies per unit, 600 -> 582 ms) */
+__device__ __forceinline__ uint4 ldcg128_now(const uint4 *p) {
+	uint4 v;
+	asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+#else
+__device__ __forceinline__ uint4 ldcg128_now(const uint4 *p) { return *p; }
+typedef uintptr_t smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(const void *p) { return (smem_addr_t)p; }
+__device__ __forceinline__ uint4 lds128(smem_addr_t a) { return *reinterpret_cast<const uint4 *>(a); }
+#endif
+
+/* one row piece: v ^= the eight table entries selected by the coefficient bytes (tables of a pair
+ * visited in opposite order by the two rows of a quarter-warp: te / to and bsel differ by row parity) */
+__device__ __forceinline__ void lean_piece(uint4 &v, u64 cf, smem_addr_t te, smem_addr_t to, unsigned bsel) {
+	const unsigned lo = __byte_perm((unsigned)cf, 0, bsel);
+	const unsigned hi = __byte_perm((unsigned)(cf >> 32), 0, bsel);
+#define LEAN_PAIR(i, cw, j0, j1)                                                       \
+	{                                                                                  \
+		const uint4 a = lds128(te + (i) * 32768 + __byte_perm(cw, 0, 0x4440 | (j0)) * 128u); \
+		const uint4 b = lds128(to + (i) * 32768 + __byte_perm(cw, 0, 0x4440 | (j1)) * 128u); \
+		v.x ^= a.x ^ b.x;                                                              \
+		v.y ^= a.y ^ b.y;                                                              \
+		v.z ^= a.z ^ b.z;                                                              \
+		v.w ^= a.w ^ b.w;                                                              \
+	}
+	LEAN_PAIR(0, lo, 0, 1)
+	LEAN_PAIR(1, lo, 2, 3)
+	LEAN_PAIR(2, hi, 0, 1)
+	LEAN_PAIR(3, hi, 2, 3)
+#undef LEAN_PAIR
+}
+
+/* a unit whose SWEEP_RU rows are all active and whose strip is not the next panel word's:
+ * p = this thread's first row piece, pcp = its first coefficient */
+__device__ __forceinline__ void lean_unit(uint4 *__restrict__ p, const u64 *__restrict__ pcp, u64 pm, smem_addr_t te,
+                                          smem_addr_t to, unsigned bsel) {
+	u64 cf[SWEEP_U];
+	uint4 d[SWEEP_U];
+#pragma unroll
+	for (int q = 0; q < SWEEP_U; q++) cf[q] = ld_weak_u64(pcp + (SWEEP_THREADS / SQ) * q) & pm;
+#pragma unroll
+	for (int q = 0; q < SWEEP_U; q++) d[q] = ldcg128_now(p + (SWEEP_THREADS / SQ) * q * SQ);
+#pragma unroll
+	for (int q = 0; q < SWEEP_U; q++) {
+		/* branch-free: a zero coefficient looks up the eight zero entries, and the row is not written
+		 * (a branch here made ptxas sink the row load below the test of its coefficient) */
+		lean_piece(d[q], cf[q], te, to, bsel);
+		if (cf[q] != 0) __stcg(p + (SWEEP_THREADS / SQ) * q * SQ, d[q]);
+	}
+}
+
+/* The list units of a sparse sweep (units [u0, u1), numbered from the first list unit): strip
+ * s0 + 1 + u / ochunks, 1024 entries of the candidate list instead of 1024 consecutive rows, one row
+ * piece at a time per thread, same tables and the same eight lookups as the streaming loop.  Kept
+ * out of line: inlined, its registers pushed spills into the streaming loop of k_forward.  Returns
+ * the phase of the tile mbarrier. */
+__device__ __noinline__ unsigned sparse_sweep(uint4 *mb, long long mp, uint4 *TD, uint4 *P, uint4 *E, u64 *bar, unsigned phase,
+                                              const uint4 *ebuf, const u64 *list, unsigned lcnt, long long u0, long long u1,
+                                              long long ochunks, int s_first, long long r1, const u64 *pc_cur, u64 pm) {
+	const int tid = threadIdx.x;
+	const int ch = tid % SQ, rl = tid / SQ;
+	const int h = rl & 1;
+	const unsigned char *Tbe = reinterpret_cast<const unsigned char *>(TD + 4 * h + ch);
+	const unsigned char *Tbo = reinterpret_cast<const unsigned char *>(TD + 4 * (1 - h) + ch);
+	const unsigned bsel = h ? 0x2301u : 0x3210u;
+	int cur = -1;
+	int s = s_first + (int)(u0 / ochunks);
+	long long chunk = u0 % ochunks;
+#pragma unroll 1
+	for (long long u = u0; u < u1; ++u, ++chunk) {
+		if (chunk == ochunks) {
+			chunk = 0;
+			++s;
+		}
+		if (s != cur) {
+			__syncthreads(); /* everyone is done with the previous tables */
+			if (tid == 0) {
+				fence_proxy_async();
+				mbar_expect_tx(bar, EBUF_Q * 16);
+				tma_bulk_g2s(E, ebuf + (long long)s * EBUF_Q, EBUF_Q * 16, bar);
+			}
+			mbar_wait(bar, phase);
+			phase ^= 1;
+			sweep_build_tables(TD, P, E, tid, nullptr, bar);
+			cur = s;
+		}
+		uint4 *strip = mb + (long long)s * mp * SQ;
+#pragma unroll 1
+		for (int q = 0; q < SWEEP_U; q++) {
+			const long long idx = chunk * SWEEP_RU + rl + (SWEEP_THREADS / SQ) * q;
+			if (idx >= (long long)lcnt) continue;
+			const long long row = (long long)__ldcg(list + 2 * idx);
+			if (row < r1) continue; /* became a pivot row of this panel */
+			const u64 cfq = ld_weak_u64(pc_cur + row) & pm;
+			if (!cfq) continue;
+			uint4 *pq = strip + row * SQ + ch;
+			uint4 v = __ldcg(pq);
+			const unsigned lo = __byte_perm((unsigned)cfq, 0, bsel);
+			const unsigned hi = __byte_perm((unsigned)(cfq >> 32), 0, bsel);
+#define TLOOK(base, off) (*reinterpret_cast<const uint4 *>((base) + (off)))
+			xor4(v, TLOOK(Tbe, 0 * 32768 + ((lo << 7) & 0x7F80u)));
+			xor4(v, TLOOK(Tbo, 0 * 32768 + ((lo >> 1) & 0x7F80u)));
+			xor4(v, TLOOK(Tbe, 1 * 32768 + ((lo >> 9) & 0x7F80u)));
+			xor4(v, TLOOK(Tbo, 1 * 32768 + ((lo >> 17) & 0x7F80u)));
+			xor4(v, TLOOK(Tbe, 2 * 32768 + ((hi << 7) & 0x7F80u)));
+			xor4(v, TLOOK(Tbo, 2 * 32768 + ((hi >> 1) & 0x7F80u)));
+			xor4(v, TLOOK(Tbe, 3 * 32768 + ((hi >> 9) & 0x7F80u)));
+			xor4(v, TLOOK(Tbo, 3 * 32768 + ((hi >> 17) & 0x7F80u)));
+#undef TLOOK
+			__stcg(pq, v);
+		}
+	}
+	return phase;
+}
+
 #define PERSIST_CTRL_BYTES 64
 #define PERSIST_SMEM (SWEEP_LINES * 128 + SWEEP_SCRATCH_BYTES + 16 + PERSIST_CTRL_BYTES)
 static_assert(sizeof(ApplySmem) <= SWEEP_LINES * 128, "the apply scratch aliases the (dead) tables");
@@ -382,6 +529,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 					__syncwarp();
 					if (tid == 0) {
 						hdr_publish(gs, w, r + S.nsel, S.pm, window_ok);
+						gs->list_cnt[w & 1] = (cnt <= PERSIST_CAND_MAX) ? cnt : 0u;
 						__threadfence();
 						st_release_gpu(&gs->sel_flag, (unsigned)w + 1);
 					}
@@ -390,7 +538,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 			/* every CTA: wait for the description, apply its share of the strips, ONE barrier */
 			__syncthreads();
 			if (tid == 0) {
-				const bool ok = persist_wait(&gs->sel_flag, (unsigned)w + 1, nullptr, gs);
+				const bool ok = persist_wait(&gs->sel_flag, (unsigned)w + 1, nullptr, gs) != 0;
 				*s_state = ok ? 1 : 0;
 			}
 			__syncthreads();
@@ -411,9 +559,25 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 		 * is followed by one that most likely needs all rows too -- the look-ahead search (17 us of one
 		 * CTA, and everybody's wait for its verdict) is skipped and the panel goes straight to the
 		 * candidate list.  A panel settled from its first rows switches the look-ahead back on. */
-		const bool try_window = (hd.x >> 31) != 0;
-
 		const long long r1 = (long long)hd.y;
+		/* Sparse sweep: when the slow path worked from a candidate list (the rows whose word of THIS
+		 * panel is non-zero) and that list is short, only the listed rows can have a non-zero
+		 * coefficient -- every strip but the one of the next panel word is swept over the list
+		 * instead of over all active rows (a unit of 1024 rows costs 8 KiB of coefficient reads even
+		 * when none of them has work: on MT19937 that was 20 us of a 44 us panel).  Row moves of the
+		 * panel are harmless: moved rows land on listed positions, and the coefficient is re-read.
+		 * The decision is taken here and again after the streaming loop (from the same words in
+		 * global memory) so that nothing of it stays live in registers across that loop. */
+		bool try_window = (hd.x >> 31) != 0;
+		long long sparse_chunks = 0; /* list chunks per strip in sparse mode, else 0 */
+		if (slow) {
+			const unsigned lc = __ldcg(&gs->list_cnt[w & 1]);
+			if (lc > 0 && (long long)lc * 4 <= m - r1) {
+				sparse_chunks = ((long long)lc + SWEEP_RU - 1) / SWEEP_RU;
+				try_window = false;
+			}
+		}
+
 		const u64 pm = ((u64)hd.w << 32) | hd.z;
 		const int k = __popcll(pm);
 		const int wn = w + 1;
@@ -439,14 +603,18 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 		const int s0 = wn >> SW_SHIFT;
 		const long long base8 = r1 & ~7LL; /* chunks start on 512-byte boundaries of the strip */
 		const long long nchunks = (m - base8 + SWEEP_RU - 1) / SWEEP_RU;
-		const long long units = (long long)(M.ns - s0) * nchunks;
+		/* chunks per strip: the strip of the next panel word always takes every active row (it hands
+		 * pc_next and the next candidate list over); the others take the list in sparse mode */
+		const long long units = nchunks + (long long)(M.ns - s0 - 1) * (sparse_chunks ? sparse_chunks : nchunks);
 		/* the CTA that owns unit 0 runs the look-ahead search (~17 us with every other warp of its SM
 		 * idle) and restarts without a prefetched tile: it is dealt PERSIST_SEL_PAD fewer units
 		 * (A/B at n = 131072, profiles/r02_ab.md: 6: 609.7, 10: 605.4, 12: 604.6, 14: 604.2, 16: 604.7 ms) */
 		const long long vpad = (has_next && try_window) ? max(0LL, min((long long)PERSIST_SEL_PAD, units / G - 1)) : 0;
 		const long long vunits = units + vpad;
 		const long long u0 = max(0LL, vunits * blockIdx.x / G - vpad);
-		const long long u1 = vunits * (blockIdx.x + 1) / G - vpad;
+		/* sparse mode: units [0, nchunks) are the rows of strip s0 (streaming loop); the list units that follow
+		 * are dealt with after it */
+		const long long u1 = sparse_chunks ? min(vunits * (blockIdx.x + 1) / G, nchunks) : vunits * (blockIdx.x + 1) / G - vpad;
 		const int nch = (wn & (SW - 1)) >> 1;
 		u64 colmask_next = ~0ULL;
 		if (wn == nw - 1 && (M.n & 63)) colmask_next = (1ULL << (M.n & 63)) - 1;
@@ -458,6 +626,11 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 			const unsigned char *Tbe = reinterpret_cast<const unsigned char *>(TD + 4 * h + ch);
 			const unsigned char *Tbo = reinterpret_cast<const unsigned char *>(TD + 4 * (1 - h) + ch);
 			const unsigned bsel = h ? 0x2301u : 0x3210u;
+#if PERSIST_LEAN_UNITS
+			const smem_addr_t te32 = smem_addr(Tbe), to32 = smem_addr(Tbo);
+			/* chunks [lean_lo, lean_hi) of a strip other than s0 lie entirely inside the active rows */
+			const long long lean_lo = (base8 >= r1) ? 0 : 1, lean_hi = (m - base8) / SWEEP_RU;
+#endif
 			int cur = -1, fetched = -1;
 			const int s_last = s0 + (int)((u1 - 1) / nchunks);
 			int s = s0 + (int)(u0 / nchunks);
@@ -494,6 +667,20 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 				const long long row0 = base8 + chunk * SWEEP_RU + rl;
 				const bool force = (s == s0);
 				uint4 *p = mb + ((long long)s * M.mp + row0) * SQ + ch;
+#if PERSIST_LEAN_UNITS
+				if (!force && chunk >= lean_lo && chunk < lean_hi) {
+					/* every consecutive lean unit of this strip in one tight loop (few live values: the
+					 * per-thread constants stay in registers instead of being re-derived per row piece) */
+					const long long nl = min(lean_hi - chunk, u1 - u);
+					const u64 *pcp = pc_cur + row0;
+#pragma unroll 1
+					for (long long i = 0; i < nl; i++, p += (long long)SWEEP_RU * SQ, pcp += SWEEP_RU)
+						lean_unit(p, pcp, pm, te32, to32, bsel);
+					u += nl - 1;
+					chunk += nl - 1;
+					continue;
+				}
+#endif
 				u64 cf[SWEEP_U];
 				uint4 d[SWEEP_U];
 				bool act[SWEEP_U];
@@ -593,20 +780,29 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 			}
 		}
 
+		if (slow) {
+			/* sparse mode (decided as at the top of the panel): this CTA's share of the list units */
+			const unsigned lc = *(volatile unsigned *)&gs->list_cnt[w & 1];
+			if (lc > 0 && (long long)lc * 4 <= m - r1) {
+				const long long oc = ((long long)lc + SWEEP_RU - 1) / SWEEP_RU;
+				const long long all = nchunks + (long long)(M.ns - s0 - 1) * oc;
+				const long long a0 = max(all * blockIdx.x / G, nchunks), a1 = all * (blockIdx.x + 1) / G;
+				if (a0 < a1)
+					phase = sparse_sweep(mb, M.mp, TD, P, E, bar, phase, ebuf, cand + (size_t)(w & 1) * PERSIST_CAND_MAX * 2, lc,
+					                     a0 - nchunks, a1 - nchunks, oc, s0 + 1, r1, pc_cur, pm);
+			}
+		}
+
 		list_ready = collect && has_next;
 		/* ---- apply(w+1) for the strips whose first-rows unit this CTA swept ------- */
 		TRACE(2); /* my units are done */
 		if (has_next) {
 			__syncthreads(); /* the tables are dead: their space is the apply scratch */
 			if (tid == 0) {
-				int state = 2; /* no look-ahead ran: the next panel takes the slow path */
-				if (try_window) {
-					state = 0;
-					if (persist_wait(&gs->sel_flag, (unsigned)wn + 1, &gs->need_full, gs))
-						state = ((int)(ld_acquire_gpu(&gs->sel_flag) - ((unsigned)wn + 1)) >= 0) ? 1 : 2;
-				}
-				__threadfence();
-				*s_state = state;
+				/* 1: the look-ahead settled the next panel, 2: it could not (or did not run: slow path), 0: fault.
+				 * The acquire load that saw the flag orders this thread; the CTA barrier below hands that
+				 * order on to the threads that read the description (ld.cg: never a stale L1 line) */
+				*s_state = try_window ? persist_wait(&gs->sel_flag, (unsigned)wn + 1, &gs->need_full, gs) : 2;
 			}
 			__syncthreads();
 			const int state = *s_state;

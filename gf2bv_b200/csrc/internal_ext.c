@@ -54,6 +54,11 @@ typedef struct {
 	void (*result_free)(gf2b200_result *);
 	int (*host_alloc)(void **, size_t);
 	void (*host_free)(void *);
+	int (*solve_open)(gf2b200_ctx *, int64_t, int64_t, gf2b200_system **);
+	int (*solve_close)(gf2b200_ctx *, gf2b200_system *, int, gf2b200_result *);
+	int (*load_begin)(gf2b200_system *, int64_t);
+	int (*load_rows)(gf2b200_system *, const uint64_t *, int64_t, int64_t);
+	int (*load_end)(gf2b200_system *, const uint64_t *);
 } shim_t;
 
 static shim_t g_shim;
@@ -156,6 +161,11 @@ static int shim_load(void) {
 	RESOLVE(result_free, "gf2b200_result_free");
 	RESOLVE(host_alloc, "gf2b200_host_alloc");
 	RESOLVE(host_free, "gf2b200_host_free");
+	RESOLVE(solve_open, "gf2b200_solve_open");
+	RESOLVE(solve_close, "gf2b200_solve_close");
+	RESOLVE(load_begin, "gf2b200_system_load_begin");
+	RESOLVE(load_rows, "gf2b200_system_load_rows");
+	RESOLVE(load_end, "gf2b200_system_load_end");
 #undef RESOLVE
 	if (s.abi_version() != GF2B200_ABI_VERSION) {
 		PyErr_Format(PyExc_RuntimeError, "gf2b200: ABI version %d, extension built for %d", s.abi_version(),
@@ -240,71 +250,130 @@ static inline int pack_equation(PyObject *eq, uint64_t *row, int64_t nw, int64_t
 /* All equations -> A (rows x nw words) and b (rows bits).  Large systems are packed
  * by several threads WITHOUT the GIL: the caller's list items are pinned by strong
  * references for the duration (ints are immutable, so their digits can be read from
- * any thread); rows are split in blocks of 64 so no two threads share a word of b.
- * The reference packs one bit at a time under the GIL (_internal.c:403-426). */
+ * any thread).  The workers take blocks of rows (multiples of 64, so no two threads share
+ * a word of b) off a shared counter; when `sys` is given, the calling thread hands every
+ * finished block to gf2b200_system_load_rows as soon as it is packed, so the H2D copy and
+ * the layout kernel of a block overlap the packing of the next ones.
+ * The reference packs one bit at a time under the GIL, then solves (_internal.c:403-426). */
 typedef struct {
 	PyObject **items;
 	uint64_t *A, *b;
 	int64_t nw, cols;
-	Py_ssize_t r0, r1;
+	Py_ssize_t rows, block_rows, nblocks;
+	Py_ssize_t next; /* next block to pack (atomic) */
+	unsigned char *done;
+	pthread_mutex_t mu;
+	pthread_cond_t cv;
 	int any_b;
-} pack_job;
+} pack_pool;
 
-static void *pack_worker(void *arg) {
-	pack_job *j = (pack_job *)arg;
+static int pack_rows(PyObject **items, uint64_t *A, uint64_t *b, int64_t nw, int64_t cols, Py_ssize_t r0,
+                     Py_ssize_t r1) {
 	int any = 0;
-	for (Py_ssize_t r = j->r0; r < j->r1; r++) {
-		if ((r & 63) == 0 || r == j->r0) j->b[r >> 6] = 0;
-		if (pack_equation(j->items[r], j->A + (size_t)r * j->nw, j->nw, j->cols)) {
-			j->b[r >> 6] |= 1ULL << (r & 63);
+	for (Py_ssize_t r = r0; r < r1; r++) {
+		if ((r & 63) == 0 || r == r0) b[r >> 6] = 0;
+		if (pack_equation(items[r], A + (size_t)r * nw, nw, cols)) {
+			b[r >> 6] |= 1ULL << (r & 63);
 			any = 1;
 		}
 	}
-	j->any_b = any;
+	return any;
+}
+
+static void *pack_worker(void *arg) {
+	pack_pool *p = (pack_pool *)arg;
+	for (;;) {
+		const Py_ssize_t blk = __atomic_fetch_add(&p->next, 1, __ATOMIC_RELAXED);
+		if (blk >= p->nblocks) break;
+		const Py_ssize_t r0 = blk * p->block_rows, r1 = r0 + p->block_rows < p->rows ? r0 + p->block_rows : p->rows;
+		const int any = pack_rows(p->items, p->A, p->b, p->nw, p->cols, r0, r1);
+		pthread_mutex_lock(&p->mu);
+		p->done[blk] = 1;
+		p->any_b |= any;
+		pthread_cond_signal(&p->cv);
+		pthread_mutex_unlock(&p->mu);
+	}
 	return NULL;
 }
 
 #define PACK_MAX_THREADS 8
 #define PACK_MIN_WORDS_PER_THREAD (1 << 20)
+#define PACK_BLOCK_BYTES (4u << 20)
 
-/* GIL held on entry and exit; items are already type-checked.  Returns any_b, or -1 on error. */
-static int pack_all(PyObject *list, Py_ssize_t rows, uint64_t *A, uint64_t *b, int64_t nw, int64_t cols) {
+/* does a system of this size take the multi-threaded, streaming path? */
+static int pack_threads(Py_ssize_t rows, int64_t nw) {
+	int64_t minw = PACK_MIN_WORDS_PER_THREAD;
+	const char *env = getenv("GF2B200_PACK_MIN_WORDS"); /* tests: take the streaming path on small systems */
+	if (env && atoll(env) > 0) minw = atoll(env);
+	int64_t n = ((int64_t)rows * nw) / minw;
+	return n > PACK_MAX_THREADS ? PACK_MAX_THREADS : (int)n;
+}
+
+/* GIL held on entry and exit; items are already type-checked.  Returns any_b, -1 on a Python
+ * error (set), or -2 when a gf2b200_system_load_rows call failed (*load_rc holds its code). */
+static int pack_all(PyObject *list, Py_ssize_t rows, uint64_t *A, uint64_t *b, int64_t nw, int64_t cols,
+                    gf2b200_system *sys, int *load_rc) {
 	PyObject **items = ((PyListObject *)list)->ob_item;
-	int nthreads = (int)(((int64_t)rows * nw) / PACK_MIN_WORDS_PER_THREAD);
-	if (nthreads > PACK_MAX_THREADS) nthreads = PACK_MAX_THREADS;
+	const int nthreads = pack_threads(rows, nw);
 	if (nthreads < 2) {
-		pack_job j = {items, A, b, nw, cols, 0, rows, 0};
-		pack_worker(&j);
-		return j.any_b;
+		const int any = pack_rows(items, A, b, nw, cols, 0, rows);
+		if (sys && (*load_rc = g_shim.load_rows(sys, A, 0, rows)) != 0) return -2;
+		return any;
 	}
 	/* the list may be mutated by other Python threads once the GIL is released:
 	 * work on a private, reference-holding copy of the item pointers */
+	pack_pool p;
+	memset(&p, 0, sizeof p);
+	const char *benv = getenv("GF2B200_PACK_BLOCK_BYTES");
+	const size_t block_bytes = (benv && atoll(benv) > 0) ? (size_t)atoll(benv) : PACK_BLOCK_BYTES;
+	p.block_rows = (Py_ssize_t)((block_bytes / ((size_t)nw * 8)) & ~(size_t)63);
+	if (p.block_rows < 64) p.block_rows = 64;
+	p.nblocks = (rows + p.block_rows - 1) / p.block_rows;
 	PyObject **held = (PyObject **)malloc((size_t)rows * sizeof(PyObject *));
-	if (!held) {
+	p.done = (unsigned char *)calloc((size_t)p.nblocks, 1);
+	if (!held || !p.done) {
+		free(held);
+		free(p.done);
 		PyErr_NoMemory();
 		return -1;
 	}
 	for (Py_ssize_t r = 0; r < rows; r++) held[r] = Py_NewRef(items[r]);
-	pack_job jobs[PACK_MAX_THREADS];
+	p.items = held;
+	p.A = A;
+	p.b = b;
+	p.nw = nw;
+	p.cols = cols;
+	p.rows = rows;
+	pthread_mutex_init(&p.mu, NULL);
+	pthread_cond_init(&p.cv, NULL);
 	pthread_t tids[PACK_MAX_THREADS];
-	int started[PACK_MAX_THREADS];
-	const Py_ssize_t blocks = (rows + 63) / 64;
+	int started = 0, rc = 0;
 	Py_BEGIN_ALLOW_THREADS
-	for (int t = 0; t < nthreads; t++) {
-		Py_ssize_t r0 = blocks * t / nthreads * 64, r1 = blocks * (t + 1) / nthreads * 64;
-		if (r1 > rows) r1 = rows;
-		jobs[t] = (pack_job){held, A, b, nw, cols, r0, r1, 0};
-		started[t] = (t + 1 < nthreads) && pthread_create(&tids[t], NULL, pack_worker, &jobs[t]) == 0;
-		if (!started[t]) pack_worker(&jobs[t]); /* the last block, or thread creation failed */
-	}
 	for (int t = 0; t < nthreads; t++)
-		if (started[t]) pthread_join(tids[t], NULL);
+		if (pthread_create(&tids[started], NULL, pack_worker, &p) == 0) started++;
+	if (!started) pack_worker(&p); /* thread creation failed: pack here */
+	/* blocks are handed over in index order: the workers take them in that order too */
+	for (Py_ssize_t blk = 0; blk < p.nblocks; blk++) {
+		pthread_mutex_lock(&p.mu);
+		while (!p.done[blk]) pthread_cond_wait(&p.cv, &p.mu);
+		pthread_mutex_unlock(&p.mu);
+		if (sys && !rc) {
+			const Py_ssize_t r0 = blk * p.block_rows, nr = r0 + p.block_rows < rows ? p.block_rows : rows - r0;
+			rc = g_shim.load_rows(sys, A + (size_t)r0 * nw, r0, nr);
+		}
+	}
+	for (int t = 0; t < started; t++) pthread_join(tids[t], NULL);
 	Py_END_ALLOW_THREADS
-	int any = 0;
-	for (int t = 0; t < nthreads; t++) any |= jobs[t].any_b;
+	pthread_mutex_destroy(&p.mu);
+	pthread_cond_destroy(&p.cv);
 	for (Py_ssize_t r = 0; r < rows; r++) Py_DECREF(held[r]);
 	free(held);
-	return any;
+	free(p.done);
+	if (rc) {
+		*load_rc = rc;
+		return -2;
+	}
+	return p.any_b;
 }
 
 /* packed little-endian words -> Python int (bit c of the int = bit c of the row;
@@ -621,13 +690,40 @@ static PyObject *m4ri_solve(PyObject *self, PyObject *const *args, Py_ssize_t na
 	uint64_t *A = stage_reserve(sl, ((size_t)rows * nw + bw) * 8);
 	if (!A) goto out;
 	uint64_t *b = A + (size_t)rows * nw; /* the packer writes every word of A and b itself */
-	const int any_b = pack_all(eqs, rows, A, b, nw, cols);
-	if (any_b < 0) goto out;
+	/* large systems: the rows stream to the GPU block by block while the packer threads are
+	 * still producing the rest (gf2b200_system_load_begin / _rows / _end) */
+	gf2b200_system *sys = NULL;
+	int rc = 0;
+	if (pack_threads(rows, nw) >= 2) {
+		Py_BEGIN_ALLOW_THREADS
+		rc = g_shim.solve_open(sl->ctx, rows, cols, &sys);
+		if (!rc && (rc = g_shim.load_begin(sys, nw)) != 0) {
+			g_shim.solve_close(sl->ctx, sys, -1, NULL);
+			sys = NULL;
+		}
+		Py_END_ALLOW_THREADS
+		if (rc) {
+			PyErr_Format(PyExc_RuntimeError, "gf2b200_solve failed (%d): %s", rc, g_shim.last_error(sl->ctx));
+			goto out;
+		}
+	}
+	const int any_b = pack_all(eqs, rows, A, b, nw, cols, sys, &rc);
+	if (any_b < 0) {
+		if (sys) g_shim.solve_close(sl->ctx, sys, -1, NULL);
+		if (any_b == -2)
+			PyErr_Format(PyExc_RuntimeError, "gf2b200_solve failed (%d): %s", rc, g_shim.last_error(sl->ctx));
+		goto out;
+	}
 
 	gf2b200_result res;
-	int rc;
 	Py_BEGIN_ALLOW_THREADS /* reference releases the GIL around M4RI too (:429) */
-	rc = g_shim.solve(sl->ctx, A, any_b ? b : NULL, rows, cols, nw, (int)mode, &res);
+	if (sys) {
+		rc = g_shim.load_end(sys, any_b ? b : NULL);
+		if (rc) g_shim.solve_close(sl->ctx, sys, -1, NULL);
+		else rc = g_shim.solve_close(sl->ctx, sys, (int)mode, &res);
+	} else {
+		rc = g_shim.solve(sl->ctx, A, any_b ? b : NULL, rows, cols, nw, (int)mode, &res);
+	}
 	Py_END_ALLOW_THREADS
 	if (rc) {
 		PyErr_Format(PyExc_RuntimeError, "gf2b200_solve failed (%d): %s", rc, g_shim.last_error(sl->ctx));
@@ -861,7 +957,7 @@ static PyObject *pack_probe(PyObject *self, PyObject *const *args, Py_ssize_t na
 			return NULL;
 		}
 	}
-	if (pack_all(args[0], rows, A, b, nw, cols) < 0) {
+	if (pack_all(args[0], rows, A, b, nw, cols, NULL, NULL) < 0) {
 		Py_DECREF(pa);
 		Py_DECREF(pb);
 		return NULL;

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GF2B200_ABI_VERSION 2
+#define GF2B200_ABI_VERSION 3
 
 #define GF2B200_OK 0
 #define GF2B200_INCONSISTENT 1 /* result.status only: system has no solution (-> None) */
@@ -124,12 +124,20 @@ int gf2b200_set_profile(gf2b200_ctx *ctx, int profile);
 int gf2b200_solve(gf2b200_ctx *ctx, const uint64_t *A, const uint64_t *b, int64_t m,
                   int64_t n, int64_t stride64, int mode, gf2b200_result *out);
 void gf2b200_result_free(gf2b200_result *res);
+/* gf2b200_solve in two halves, for a caller that streams the rows in between
+ * (gf2b200_system_load_begin / _rows / _end): open hands out the context's cached system of
+ * that shape (or a new one); close eliminates, fetches the result and returns the system to the
+ * cache.  close with mode < 0 gives the system up without solving (a load failed). */
+int gf2b200_solve_open(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2b200_system **out);
+int gf2b200_solve_close(gf2b200_ctx *ctx, gf2b200_system *sys, int mode, gf2b200_result *out);
 
 /* ---- device-resident systems -------------------------------------------- */
 /* m, n are GLOBAL sizes; with a dist context each rank holds rows
  * [rank*m/world, (rank+1)*m/world) of the global system.  On a sharded system
- * (dist or loopback) system_result(mode 1) runs one blocked back-substitution per
- * free column; on a dist context every rank must call it and gets the whole basis. */
+ * (dist or loopback) system_result(mode 1) runs the same blocked multi-right-hand-side
+ * triangular solve as on one GPU, every shard on its own echelon rows, with one small
+ * exchange per backward panel; on a dist context every rank must call it and gets the
+ * whole basis. */
 int gf2b200_system_create(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2b200_system **out);
 void gf2b200_system_destroy(gf2b200_system *sys);
 int64_t gf2b200_system_local_rows(const gf2b200_system *sys);
@@ -139,6 +147,16 @@ int gf2b200_system_load_host(gf2b200_system *sys, const uint64_t *A, const uint6
                              int64_t stride64);
 int gf2b200_system_load_device(gf2b200_system *sys, const uint64_t *dA, const uint64_t *db,
                                int64_t stride64);
+/* The same load handed over in blocks while the caller is still PRODUCING the rows: the
+ * extension packs PyLongs on worker threads and passes each finished block on, so the H2D copy
+ * and the layout kernel of a block overlap the packing of the next (the reference packs
+ * everything, then calls M4RI: _internal.c:403-426, then :433).  begin; any number of
+ * load_rows (local rows [row0, row0 + nrows), A_rows points at row row0, any order, no overlap;
+ * the host memory must stay valid until load_end returns); end takes b (the packed bits of the
+ * local rows, NULL = homogeneous) and returns when every copy has left the host buffers. */
+int gf2b200_system_load_begin(gf2b200_system *sys, int64_t stride64);
+int gf2b200_system_load_rows(gf2b200_system *sys, const uint64_t *A_rows, int64_t row0, int64_t nrows);
+int gf2b200_system_load_end(gf2b200_system *sys, const uint64_t *b);
 /* Dense synthetic system of SURVEY.md 8(d) generated in HBM: word(i,w) =
  * splitmix64-mix(seed + PHI*(i*ceil(n/64) + w + 1)), b = A x*, x* from seed^0xB200. */
 int gf2b200_system_generate(gf2b200_system *sys, uint64_t seed);

@@ -126,6 +126,33 @@ def test_random_systems_match_oracle_through_m4ri_solve():
                    [want.get(i) for i in range(1 << want.dimension)]
 
 
+def test_streamed_pack_matches_oracle(monkeypatch):
+    """large systems are packed by worker threads in blocks that stream to the GPU while the rest is
+    still being packed (gf2b200_system_load_begin / _rows / _end); the thresholds are lowered so the
+    path runs on small systems: full rank, rank-deficient, inconsistent, homogeneous, both modes"""
+    monkeypatch.setenv("GF2B200_PACK_MIN_WORDS", "64")
+    monkeypatch.setenv("GF2B200_PACK_BLOCK_BYTES", "4096")
+    rnd = random.Random(77)
+    for cols, rows, cap in [(300, 700, None), (257, 1000, 100), (640, 641, None), (130, 900, 0)]:
+        basis = [rnd.getrandbits(cols + 1) & ~1 for _ in range(cols if cap is None else cap)]
+        eqs = []
+        for _ in range(rows):
+            v = 0
+            for bv in rnd.sample(basis, min(len(basis), 7)):
+                v ^= bv
+            eqs.append(v)
+        x = rnd.getrandbits(cols)
+        consistent = [(e & ~1) | (bin((e >> 1) & x).count("1") & 1) for e in eqs]
+        noisy = [e ^ (rnd.random() < 0.02) for e in consistent]
+        for sysm in (consistent, noisy, eqs):
+            for mode in (0, 1):
+                got, want = _internal.m4ri_solve(sysm, cols, mode), oracle.m4ri_solve(sysm, cols, mode)
+                if mode == 0:
+                    assert got == want
+                else:
+                    _same_space(got, want)
+
+
 def test_dimension_too_large_error_carries_space():
     lin = gf2bv.LinearSystem([40])
     (v,) = lin.gens()

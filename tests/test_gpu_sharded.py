@@ -72,11 +72,12 @@ def test_sharded_pivots_concentrated_in_one_shard(sharded):
 
 @pytest.mark.parametrize("m,n,cap", [
     (70, 64, None), (300, 200, 190), (700, 640, 620), (2200, 2110, None), (2300, 2100, 2070),
-    # one back-substitution per free column: the large nullities are left to the GPU
+    # (large nullities: minutes on the emulated kernels, instant on the GPU)
     pytest.param(1300, 2100, 900, id="bignull-1300-2100-900"), pytest.param(64, 4096, 20, id="bignull-64-4096-20"),
     pytest.param(1111, 999, 1, id="bignull-1111-999-1")])
 def test_sharded_kernel_basis(sharded, m, n, cap):
-    """mode 1 on a sharded system: one blocked back-substitution per free column;
+    """mode 1 on a sharded system: the blocked multi-right-hand-side triangular solve, every shard on
+    its own echelon rows, one exchange per backward panel (basis_sharded, gf2b200.cu);
     basis values AND order (M4RI's sigma order) equal the oracle's, and a mode-0
     result taken afterwards is still the particular solution"""
     rnd = random.Random(cap or 0 + m)
@@ -91,6 +92,23 @@ def test_sharded_kernel_basis(sharded, m, n, cap):
     _check(ss.result(0), want)
     got2 = ss.result(1)
     assert np.array_equal(got2.basis, want.basis) and np.array_equal(got2.origin, want.origin)
+
+
+def test_sharded_kernel_basis_stats(sharded):
+    """the sharded kernel basis is ONE blocked solve: a backward sweep per panel with pivots, not a
+    back-substitution per free column"""
+    rnd = random.Random(21)
+    m, n, cap = 900, 1400, 500
+    A, b = _rand_system(rnd, m, n, rank_cap=cap, consistent=True)
+    ss = sharded.system(m, n)
+    ss.load_host(A, b)
+    ss.eliminate()
+    got = ss.result(1)
+    want = oracle.solve_packed(A, b, n, 1)
+    _check(got, want)
+    assert np.array_equal(got.basis, want.basis)
+    st = ss.stats()
+    assert 0 < st["basis_panels"] <= (n + 63) // 64 and st["basis_sweep_bytes"] > 0
 
 
 def test_sharded_kernel_basis_homogeneous(sharded):

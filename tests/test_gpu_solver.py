@@ -104,6 +104,51 @@ def test_sparse_and_zero_rows(ctx, density):
     assert not got.origin.any()
 
 
+def _near_triangular(seed, m, n, extra):
+    """sparse, near-triangular, rows shuffled (the MT19937 class of systems): row i has a
+    one near column i*n/m and `extra` more anywhere -- every panel of k_forward takes the all-rows
+    search, collects candidate lists and sweeps the far strips over the list (sparse_sweep)"""
+    rng = np.random.default_rng(seed)
+    nw = (n + 63) // 64
+    A = np.zeros((m, nw), dtype=np.uint64)
+    rows = np.repeat(np.arange(m), extra + 1)
+    cols = np.concatenate([np.minimum(n - 1, np.arange(m) * n // m)[:, None],
+                           rng.integers(0, n, size=(m, extra))], axis=1).ravel()
+    np.bitwise_xor.at(A, (rows, cols // 64), np.uint64(1) << (cols % 64).astype(np.uint64))
+    A = A[rng.permutation(m)]
+    x = rng.integers(0, 2, size=n).astype(np.int64)
+    bits = np.unpackbits(A.view(np.uint8), axis=1, bitorder="little")[:, :n]
+    bp = np.zeros(((m + 63) // 64) * 64, dtype=bool)
+    bp[:m] = (bits.astype(np.int64) @ x) % 2 == 1
+    return A, np.packbits(bp, bitorder="little").view(np.uint64).copy()
+
+
+@pytest.mark.parametrize("seed,m,n,extra", [(0, 6000, 5000, 3), (1, 9000, 4000, 2), (2, 5000, 5000, 1)])
+def test_sparse_near_triangular_matches_oracle(ctx, seed, m, n, extra):
+    A, b = _near_triangular(seed, m, n, extra)
+    for mode in (0, 1):
+        _assert_same(ctx.solve(A, b, n, mode), oracle.solve_packed(A, b, n, mode), mode)
+
+
+def test_load_in_blocks_any_order(ctx):
+    """gf2b200_system_load_begin / _rows / _end: blocks in any order give the system load_host gives;
+    also through 3 loopback shards (a block may straddle shards)"""
+    rnd = random.Random(5)
+    m, n = 1500, 1100
+    A, b = _rand_system(rnd, m, n, rank_cap=800, consistent=True)
+    want = oracle.solve_packed(A, b, n, 1)
+    blocks = [(r, min(192, m - r)) for r in range(0, m, 192)]
+    rnd.shuffle(blocks)
+    for c in (ctx, _shim.Context(0, shards=3)):
+        s = c.system(m, n)
+        s.load_host_blocks(A, b, blocks)
+        s.eliminate()
+        _assert_same(s.result(1), want, 1)
+        s.load_host_blocks(A, None, blocks[::-1])
+        s.eliminate()
+        _assert_same(s.result(1), oracle.solve_packed(A, None, n, 1), 1)
+
+
 def test_all_zero_and_identity(ctx):
     n = 200
     nw = (n + 63) // 64

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert set(_shim.EXPORTS) == declared
-    assert lib.gf2b200_abi_version() == 2
+    assert lib.gf2b200_abi_version() == 3
 
 
 def test_ctypes_mirrors_match_header_structs():
