@@ -756,6 +756,96 @@ static_assert(SWEEP_THREADS == 8 * 32 * 4, "one partial-table item per thread; (
 #define SWEEP_TAIL_SELECT 0
 #endif
 
+#if SW == 8
+/* ---- the lean streaming unit (64-byte strips) -------------------------------------------
+ * ncu on the first k_forward (profiles/r02r_forward_ncu.md): besides l1tex (the lookups) and HBM
+ * the ALU pipe is a co-limiter of the streaming loop -- 450 SASS instructions per unit and
+ * thread where the arithmetic needs ~220: row-range predicates, the look-ahead / candidate-list
+ * branches and, per lookup, the generic-to-shared address conversion the compiler re-derives
+ * when registers are short (S2R CgaCtaId + LEA).  Units that lie entirely inside the active rows
+ * of a strip other than the next panel word's -- all but a few hundred of the 32768 units of a
+ * large panel -- take this path instead: no predicates, 32-bit shared-memory addresses computed
+ * once per thread, one byte extract (ALU) + one multiply-add (FMA pipe) per lookup: 275 instructions
+ * per unit, 651 -> 620 ms at n = 131072 on one box (profiles/r02_ab.md, calls S and T).  Measured and
+ * dropped there: the same loop behind a call boundary (221 instructions but 642 ms), all eight loads
+ * of a unit issued before the first lookup (691 ms: ptxas' own schedule, which requests row piece
+ * q + 2 while piece q is looked up, is the better one), a rolling pipeline that requests unit i + 1
+ * piece by piece (731 ms) and a TMA bulk prefetch of the next units into L2 (650 - 670 ms). */
+#ifndef SWEEP_LEAN_UNITS
+#define SWEEP_LEAN_UNITS 1
+#endif
+
+#ifndef GF2_EMU
+/* a plain (weak, L1-allocating) global load the compiler can neither drop nor turn into ld.global.nc */
+__device__ __forceinline__ u64 ld_weak_u64(const u64 *p) {
+	u64 v;
+	asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p));
+	return v;
+}
+typedef unsigned smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(const void *p) { return (smem_addr_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 lds128(smem_addr_t a) {
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+	return v;
+}
+/* a row load the compiler can neither sink below the test of its coefficient nor drop (the row
+ * loads must not wait for the coefficient: two chained L2 latencies per unit, 600 -> 582 ms) */
+__device__ __forceinline__ uint4 ldcg128_now(const uint4 *p) {
+	uint4 v;
+	asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+#else
+__device__ __forceinline__ u64 ld_weak_u64(const u64 *p) { return *p; }
+__device__ __forceinline__ uint4 ldcg128_now(const uint4 *p) { return *p; }
+typedef uintptr_t smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(const void *p) { return (smem_addr_t)p; }
+__device__ __forceinline__ uint4 lds128(smem_addr_t a) { return *reinterpret_cast<const uint4 *>(a); }
+#endif
+
+/* one row piece: v ^= the eight table entries selected by the coefficient bytes (tables of a pair
+ * visited in opposite order by the two rows of a quarter-warp: te / to and bsel differ by row parity) */
+__device__ __forceinline__ void lean_piece(uint4 &v, u64 cf, smem_addr_t te, smem_addr_t to, unsigned bsel) {
+	const unsigned lo = __byte_perm((unsigned)cf, 0, bsel);
+	const unsigned hi = __byte_perm((unsigned)(cf >> 32), 0, bsel);
+#define LEAN_PAIR(i, cw, j0, j1)                                                       \
+	{                                                                                  \
+		const uint4 a = lds128(te + (i) * 32768 + __byte_perm(cw, 0, 0x4440 | (j0)) * 128u); \
+		const uint4 b = lds128(to + (i) * 32768 + __byte_perm(cw, 0, 0x4440 | (j1)) * 128u); \
+		v.x ^= a.x ^ b.x;                                                              \
+		v.y ^= a.y ^ b.y;                                                              \
+		v.z ^= a.z ^ b.z;                                                              \
+		v.w ^= a.w ^ b.w;                                                              \
+	}
+	LEAN_PAIR(0, lo, 0, 1)
+	LEAN_PAIR(1, lo, 2, 3)
+	LEAN_PAIR(2, hi, 0, 1)
+	LEAN_PAIR(3, hi, 2, 3)
+#undef LEAN_PAIR
+}
+
+/* a unit whose SWEEP_RU rows are all active and whose strip is not the next panel word's:
+ * p = this thread's first row piece, pcp = its first coefficient */
+__device__ __forceinline__ void lean_unit(uint4 *__restrict__ p, const u64 *__restrict__ pcp, u64 pm, smem_addr_t te,
+                                          smem_addr_t to, unsigned bsel) {
+	u64 cf[SWEEP_U];
+	uint4 d[SWEEP_U];
+#pragma unroll
+	for (int q = 0; q < SWEEP_U; q++) cf[q] = ld_weak_u64(pcp + (SWEEP_THREADS / SQ) * q) & pm;
+#pragma unroll
+	for (int q = 0; q < SWEEP_U; q++) d[q] = ldcg128_now(p + (SWEEP_THREADS / SQ) * q * SQ);
+#pragma unroll
+	for (int q = 0; q < SWEEP_U; q++) {
+		/* branch-free: a zero coefficient looks up the eight zero entries, and the row is not written
+		 * (a branch here made ptxas sink the row load below the test of its coefficient) */
+		lean_piece(d[q], cf[q], te, to, bsel);
+		if (cf[q] != 0) __stcg(p + (SWEEP_THREADS / SQ) * q * SQ, d[q]);
+	}
+}
+
+#endif /* SW == 8 */
+
 __device__ __forceinline__ void
 sweep_body(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
            u64 *__restrict__ pc_next, const uint4 *__restrict__ ebuf, int w, int s0,
@@ -871,6 +961,19 @@ sweep_body(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_c
 		const long long row0 = r1 + chunk * SWEEP_RU + rl;
 		const bool force = (s == snext);
 		uint4 *p = mb + ((long long)s * M.mp + row0) * SQ + ch;
+#if SW == 8 && SWEEP_LEAN_UNITS && !SWEEP_EARLY_LOADS
+		if (!force && chunk < rows / SWEEP_RU) {
+			/* every consecutive unit of this strip whose SWEEP_RU rows are all active */
+			const long long nl = min(rows / SWEEP_RU - chunk, u1 - u);
+			const smem_addr_t te32 = smem_addr(Tbe), to32 = smem_addr(Tbo);
+			const u64 *pcp = pc_cur + row0;
+#pragma unroll 1
+			for (long long i = 0; i < nl; i++, p += (long long)SWEEP_RU * SQ, pcp += SWEEP_RU)
+				lean_unit(p, pcp, pm, te32, to32, bsel);
+			u += nl - 1;
+			continue;
+		}
+#endif
 		u64 cf[SWEEP_U];
 		uint4 d[SWEEP_U];
 		bool act[SWEEP_U];

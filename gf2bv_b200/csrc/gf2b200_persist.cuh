@@ -103,6 +103,9 @@ __device__ __forceinline__ void hdr_publish(GridSync *gs, int w, long long r1, u
  * append every row whose new panel word is non-zero to a candidate list (warp-aggregated
  * atomics); CTA 0 then scans that list (a few % of the rows on MT19937-class systems)
  * instead of the whole column.  More than PERSIST_CAND_MAX candidates: full scan. */
+#ifndef PERSIST_GJ_SEARCH
+#define PERSIST_GJ_SEARCH 1
+#endif
 #ifndef PERSIST_SEL_PAD
 #define PERSIST_SEL_PAD 14
 #endif
@@ -130,14 +133,7 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 /* generic-proxy writes (other CTAs' st.global, made visible by the acquire before this)
  * before the async-proxy read of the bulk copy that follows */
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-/* a plain (weak, L1-allocating) global load the compiler can neither drop nor turn into ld.global.nc */
-__device__ __forceinline__ u64 ld_weak_u64(const u64 *p) {
-	u64 v;
-	asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p));
-	return v;
-}
 #else
-__device__ __forceinline__ u64 ld_weak_u64(const u64 *p) { return *p; }
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 __device__ __forceinline__ unsigned long long gtimer_ns() { return (unsigned long long)(emu_now_ms() * 1e6); }
@@ -174,7 +170,7 @@ __device__ __forceinline__ bool grid_barrier(GridSync *gs, int *s_ok) {
 			atomicExch(&gs->count, 0u);
 			st_release_gpu(&gs->gen, g + 1); /* cumulative: orders everything this thread observed */
 		} else {
-			ok = persist_wait(&gs->gen, g + 1, nullptr, gs); /* acquire loads */
+			ok = persist_wait(&gs->gen, g + 1, nullptr, gs) != 0; /* acquire loads */
 		}
 		*s_ok = (ok && !*(volatile int *)&gs->fault) ? 1 : 0;
 	}
@@ -256,6 +252,109 @@ __device__ __forceinline__ void window_search(SelectSmem &S, long long base8, u6
 	__syncwarp();
 }
 
+/* The same search as a Gauss-Jordan elimination, for the usual case that the window holds a full
+ * set of pivots and the panel has all 64 columns.  window_search inserts ~66 rows one after the
+ * other, ~100 dependent instructions each: 14.5 us on the critical path of every small panel
+ * (profiles/r02_trace.md).  Here lane L holds window slots L and L + 32 as ROWS (value v, transform t
+ * over the 64 slots):
+ *   phase A  the first 64 slots are eliminated column by column: two ballots find a row that is
+ *            not a pivot yet and has a 1 in column c, two 64-bit shuffles broadcast it, every other
+ *            row with a 1 there absorbs it (~25 instructions per column);
+ *   phase B  a random 64 x 64 block has full rank with probability 0.29 only (expected defect 0.85):
+ *            the missing columns come from the following slots, each candidate reduced against the
+ *            basis with one lane-local selection + a warp XOR, and a row that survives moves into
+ *            a slot phase A left without a pivot (its index there is its "selected row" number).
+ * Which rows are selected does not matter (the pivot COLUMNS are the invariant);
+ * selected row l = slot l, TB[c] = transform of the row whose pivot is column c.  Returns with
+ * S.pm != all-ones when the window does not hold a full set: the caller then takes the all-rows
+ * search, as before. */
+__device__ __forceinline__ void window_search_gj(SelectSmem &S, long long base8, int lane) {
+	for (int c = lane; c < 64; c += 32) {
+		S.sel[c] = -1;
+		S.topsel[c] = 0;
+	}
+	u64 v0 = S.qv[lane], v1 = S.qv[lane + 32];
+	u64 t0 = 1ULL << lane, t1 = 1ULL << (lane + 32);
+	int c0 = -1, c1 = -1; /* pivot column of my two rows, -1: none (yet) */
+	u64 pm = 0;
+#pragma unroll 1
+	for (int c = 0; c < 64; c++) {
+		const bool b0 = (v0 >> c) & 1, b1 = (v1 >> c) & 1;
+		const unsigned f0 = __ballot_sync(0xffffffffu, b0 && c0 < 0), f1 = __ballot_sync(0xffffffffu, b1 && c1 < 0);
+		if (!(f0 | f1)) continue; /* no row of this block has a pivot in column c */
+		const bool low = f0 != 0;
+		const int src = __ffs((int)(low ? f0 : f1)) - 1;
+		const u64 pv = shfl64(low ? v0 : v1, src), pt = shfl64(low ? t0 : t1, src);
+		const bool me0 = low && lane == src, me1 = !low && lane == src;
+		if (b0 && !me0) {
+			v0 ^= pv;
+			t0 ^= pt;
+		}
+		if (b1 && !me1) {
+			v1 ^= pv;
+			t1 ^= pt;
+		}
+		if (me0) c0 = c;
+		if (me1) c1 = c;
+		pm |= 1ULL << c;
+	}
+	/* phase B: the columns still missing, from the slots that follow */
+	for (int g = 2; g < SWEEP_RU / 32 && pm != ~0ULL; g++) {
+		const u64 mine = S.qv[32 * g + lane];
+		unsigned bal = __ballot_sync(0xffffffffu, mine != 0);
+		while (bal && pm != ~0ULL) {
+			const int src = __ffs((int)bal) - 1;
+			bal &= bal - 1;
+			const u64 x = shfl64(mine, src);
+			/* the basis is reduced: x loses exactly the rows whose pivot column it has a 1 in */
+			const bool u0 = c0 >= 0 && ((x >> c0) & 1), u1 = c1 >= 0 && ((x >> c1) & 1);
+			const u64 xr = x ^ warp_xor64((u0 ? v0 : 0) ^ (u1 ? v1 : 0));
+			if (!xr) continue; /* dependent on the rows selected so far */
+			const int c = __ffsll((long long)xr) - 1;
+			const unsigned h0 = __ballot_sync(0xffffffffu, c0 < 0), h1 = __ballot_sync(0xffffffffu, c1 < 0);
+			const bool low = h0 != 0; /* a slot without a pivot exists: fewer than 64 pivots so far */
+			const int hl = __ffs((int)(low ? h0 : h1)) - 1;
+			const int slot = hl + (low ? 0 : 32);
+			const u64 tn = warp_xor64((u0 ? t0 : 0) ^ (u1 ? t1 : 0)) ^ (1ULL << slot);
+			if (c0 >= 0 && ((v0 >> c) & 1)) {
+				v0 ^= xr;
+				t0 ^= tn;
+			}
+			if (c1 >= 0 && ((v1 >> c) & 1)) {
+				v1 ^= xr;
+				t1 ^= tn;
+			}
+			if (lane == hl) {
+				if (low) {
+					v0 = xr;
+					t0 = tn;
+					c0 = c;
+				} else {
+					v1 = xr;
+					t1 = tn;
+					c1 = c;
+				}
+				S.sel[slot] = (int)(base8 + 32 * g + src);
+			}
+			pm |= 1ULL << c;
+		}
+	}
+	/* phase A pivots sit in their own slots; rows that moved in during phase B wrote S.sel themselves */
+	if (c0 >= 0) {
+		S.TB[c0] = t0;
+		if (S.sel[lane] < 0) S.sel[lane] = (int)(base8 + lane);
+	}
+	if (c1 >= 0) {
+		S.TB[c1] = t1;
+		if (S.sel[lane + 32] < 0) S.sel[lane + 32] = (int)(base8 + lane + 32);
+	}
+	if (lane == 0) {
+		S.pm = pm;
+		S.nsel = __popcll(pm);
+	}
+	__syncwarp();
+}
+
 /* Shared-memory image of the panel description an apply needs. */
 struct ApplySmem {
 	uint4 Sel[4][64][SQ]; /* four strips at a time, 256 threads each */
@@ -318,86 +417,6 @@ __device__ __forceinline__ void persist_apply(const Mat &M, const PanelDesc *pdn
 			if (rr < nmove) __stcg(mb + (sb + A.dst[rr]) * SQ + ch, A.Dis[g][rr][ch]);
 		}
 		__syncthreads();
-	}
-}
-
-/* ---- the lean streaming unit ---------------------------------------------------------
- * ncu on the first k_forward (profiles/r02r_forward_ncu.md): besides l1tex (the lookups) and HBM
- * the ALU pipe is a co-limiter of the streaming loop -- 450 SASS instructions per unit and
- * thread where the arithmetic needs ~220: row-range predicates, the look-ahead / candidate-list
- * branches and, per lookup, the generic-to-shared address conversion the compiler re-derives
- * when registers are short (S2R CgaCtaId + LEA).  Units that lie entirely inside the active rows
- * of a strip other than the next panel word's -- all but a few hundred of the 32768 units of a
- * large panel -- take this path instead: no predicates, 32-bit shared-memory addresses computed
- * once per thread, one byte extract (ALU) + one multiply-add (FMA pipe) per lookup: 275 instructions
- * per unit, 651 -> 620 ms at n = 131072 on one box (profiles/r02_ab.md, calls S and T).  Measured and
- * dropped there: the same loop behind a call boundary (221 instructions but 642 ms), all eight loads
- * of a unit issued before the first lookup (691 ms: ptxas' own schedule, which requests row piece
- * q + 2 while piece q is looked up, is the better one), a rolling pipeline that requests unit i + 1
- * piece by piece (731 ms) and a TMA bulk prefetch of the next units into L2 (650 - 670 ms). */
-#ifndef PERSIST_LEAN_UNITS
-#define PERSIST_LEAN_UNITS 1
-#endif
-
-#ifndef GF2_EMU
-typedef unsigned smem_addr_t;
-__device__ __forceinline__ smem_addr_t smem_addr(const void *p) { return (smem_addr_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint4 lds128(smem_addr_t a) {
-	uint4 v;
-	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-	return v;
-}
-/* a row load the compiler can neither sink below the test of its coefficient nor drop (the row
- * loads must not wait for the coefficient: two chained L2 latencies per unit, 600 -> 582 ms) */
-__device__ __forceinline__ uint4 ldcg128_now(const uint4 *p) {
-	uint4 v;
-	asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-	return v;
-}
-#else
-__device__ __forceinline__ uint4 ldcg128_now(const uint4 *p) { return *p; }
-typedef uintptr_t smem_addr_t;
-__device__ __forceinline__ smem_addr_t smem_addr(const void *p) { return (smem_addr_t)p; }
-__device__ __forceinline__ uint4 lds128(smem_addr_t a) { return *reinterpret_cast<const uint4 *>(a); }
-#endif
-
-/* one row piece: v ^= the eight table entries selected by the coefficient bytes (tables of a pair
- * visited in opposite order by the two rows of a quarter-warp: te / to and bsel differ by row parity) */
-__device__ __forceinline__ void lean_piece(uint4 &v, u64 cf, smem_addr_t te, smem_addr_t to, unsigned bsel) {
-	const unsigned lo = __byte_perm((unsigned)cf, 0, bsel);
-	const unsigned hi = __byte_perm((unsigned)(cf >> 32), 0, bsel);
-#define LEAN_PAIR(i, cw, j0, j1)                                                       \
-	{                                                                                  \
-		const uint4 a = lds128(te + (i) * 32768 + __byte_perm(cw, 0, 0x4440 | (j0)) * 128u); \
-		const uint4 b = lds128(to + (i) * 32768 + __byte_perm(cw, 0, 0x4440 | (j1)) * 128u); \
-		v.x ^= a.x ^ b.x;                                                              \
-		v.y ^= a.y ^ b.y;                                                              \
-		v.z ^= a.z ^ b.z;                                                              \
-		v.w ^= a.w ^ b.w;                                                              \
-	}
-	LEAN_PAIR(0, lo, 0, 1)
-	LEAN_PAIR(1, lo, 2, 3)
-	LEAN_PAIR(2, hi, 0, 1)
-	LEAN_PAIR(3, hi, 2, 3)
-#undef LEAN_PAIR
-}
-
-/* a unit whose SWEEP_RU rows are all active and whose strip is not the next panel word's:
- * p = this thread's first row piece, pcp = its first coefficient */
-__device__ __forceinline__ void lean_unit(uint4 *__restrict__ p, const u64 *__restrict__ pcp, u64 pm, smem_addr_t te,
-                                          smem_addr_t to, unsigned bsel) {
-	u64 cf[SWEEP_U];
-	uint4 d[SWEEP_U];
-#pragma unroll
-	for (int q = 0; q < SWEEP_U; q++) cf[q] = ld_weak_u64(pcp + (SWEEP_THREADS / SQ) * q) & pm;
-#pragma unroll
-	for (int q = 0; q < SWEEP_U; q++) d[q] = ldcg128_now(p + (SWEEP_THREADS / SQ) * q * SQ);
-#pragma unroll
-	for (int q = 0; q < SWEEP_U; q++) {
-		/* branch-free: a zero coefficient looks up the eight zero entries, and the row is not written
-		 * (a branch here made ptxas sink the row load below the test of its coefficient) */
-		lean_piece(d[q], cf[q], te, to, bsel);
-		if (cf[q] != 0) __stcg(p + (SWEEP_THREADS / SQ) * q * SQ, d[q]);
 	}
 }
 
@@ -626,7 +645,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 			const unsigned char *Tbe = reinterpret_cast<const unsigned char *>(TD + 4 * h + ch);
 			const unsigned char *Tbo = reinterpret_cast<const unsigned char *>(TD + 4 * (1 - h) + ch);
 			const unsigned bsel = h ? 0x2301u : 0x3210u;
-#if PERSIST_LEAN_UNITS
+#if SWEEP_LEAN_UNITS
 			const smem_addr_t te32 = smem_addr(Tbe), to32 = smem_addr(Tbo);
 			/* chunks [lean_lo, lean_hi) of a strip other than s0 lie entirely inside the active rows */
 			const long long lean_lo = (base8 >= r1) ? 0 : 1, lean_hi = (m - base8) / SWEEP_RU;
@@ -667,7 +686,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 				const long long row0 = base8 + chunk * SWEEP_RU + rl;
 				const bool force = (s == s0);
 				uint4 *p = mb + ((long long)s * M.mp + row0) * SQ + ch;
-#if PERSIST_LEAN_UNITS
+#if SWEEP_LEAN_UNITS
 				if (!force && chunk >= lean_lo && chunk < lean_hi) {
 					/* every consecutive lean unit of this strip in one tight loop (few live values: the
 					 * per-thread constants stay in registers instead of being re-derived per row piece) */
@@ -762,7 +781,14 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 					TRACE(6);
 					if (tid < 32) {
 						const long long lim = min(m, base8 + (long long)SWEEP_RU);
-						window_search(S, base8, colmask_next, tid);
+						/* the Gauss-Jordan form needs all 64 columns and is only good for a full set of
+						 * pivots: the last panel of an n that is no multiple of 64 and the last window of
+						 * the matrix (whose partial result is final) keep the row-by-row search */
+#if PERSIST_GJ_SEARCH
+						if (colmask_next == ~0ULL && lim < m) window_search_gj(S, base8, tid);
+						else
+#endif
+							window_search(S, base8, colmask_next, tid);
 						TRACE_W0(1); /* (the search CTA's slot 1 is re-used: window search done) */
 						const bool final_ = (S.pm == colmask_next || lim == m);
 						if (final_) select_finalize(S, pc_next, wn, r1, st, pdn, hist_r, hist_pm);
