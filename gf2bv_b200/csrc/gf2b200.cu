@@ -216,8 +216,10 @@ static int ctx_init(gf2b200_ctx **out, int device) {
 	 * (cooperative launch); GF2B200_FORWARD=launches keeps the per-panel launch chain */
 	if (e == cudaSuccess) e = cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, PERSIST_SMEM);
 	if (e == cudaSuccess) {
+		/* 1: k_forward for systems below PERSIST_AUTO_BYTES (default), 2: always (GF2B200_FORWARD=persist),
+		 * 0: never (GF2B200_FORWARD=launches) */
 		const char *fw = getenv("GF2B200_FORWARD");
-		c->persist = !(fw && !strcmp(fw, "launches"));
+		c->persist = (fw && !strcmp(fw, "launches")) ? 0 : (fw && !strcmp(fw, "persist")) ? 2 : 1;
 #ifndef GF2_EMU
 		int coop = 0, per_sm = 0;
 		if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess) coop = 0;
@@ -774,6 +776,10 @@ static int forward_single(gf2b200_system *sys, long long *launches) {
 }
 
 #if SW == 8
+/* systems of at least this many bytes take the launch chain unless GF2B200_FORWARD says otherwise */
+#ifndef PERSIST_AUTO_BYTES
+#define PERSIST_AUTO_BYTES (256.0 * 1024.0 * 1024.0)
+#endif
 /* forward elimination of a one-shard system as ONE cooperative kernel (gf2b200_persist.cuh) */
 static int forward_single_persist(gf2b200_system *sys, long long *launches) {
 	gf2b200_ctx *ctx = sys->ctx;
@@ -934,7 +940,15 @@ extern "C" int gf2b200_system_eliminate(gf2b200_system *sys) {
 	}
 	bool persist = false;
 #if SW == 8
-	persist = !sharded && ctx->persist && sys->sh[0].d_gs;
+	/* Which forward elimination: the persistent kernel saves 2 - 6 us of fixed cost per panel, the
+	 * launch chain's k_sweep streams ~3 % faster (same source, but ptxas schedules the loop better
+	 * outside the large persistent kernel): per-panel sweeps longer than ~50 us favour the chain.
+	 * Measured on one box (profiles/r02_ab.md, calls U - W; k_forward / launch chain): n = 8192
+	 * 3.93 / 4.60 ms, n = 32768 21.2 / 22.2 ms, n = 65536 96.3 / 91.6 ms, n = 131072 619 / 601 ms.
+	 * (Programmatic dependent launch between the kernels of the chain was measured too: faster at
+	 * n = 8192, 4.08 ms, but slower from n = 65536 up, 95.1 and 622 ms -- not kept.) */
+	persist = !sharded && ctx->persist && sys->sh[0].d_gs &&
+	          (ctx->persist == 2 || (double)sys->sh[0].M.mp * sys->sh[0].M.ns * SBYTES < PERSIST_AUTO_BYTES);
 #endif
 	int rc;
 	if (sharded) rc = forward_sharded(sys, &launches, &xbytes);

@@ -484,6 +484,73 @@ __device__ __noinline__ unsigned sparse_sweep(uint4 *mb, long long mp, uint4 *TD
 	return phase;
 }
 
+/* What a CTA derives from the header of a panel: its share [u0, u1) of the panel's work units and
+ * the geometry behind it.  Computed before the streaming loop and AGAIN after it, from words
+ * re-read from global memory: written once and used on both sides of the loop, these values
+ * stayed in registers across it, and ptxas paid for them inside the loop -- it re-derived the
+ * per-thread constants for every row piece and staggered the coefficient loads (275 instructions
+ * per lean unit where k_sweep, with the same source, needs 229: the launch chain had become
+ * faster than the persistent kernel at n = 131072, 606 against 622 ms, profiles/r02_ab.md call U). */
+struct PanelGeo {
+	long long r1, base8, nchunks, u0, u1;
+	long long sparse_chunks; /* list chunks per strip in sparse mode, else 0 */
+	u64 pm;
+	int s0;
+	bool try_window;
+};
+
+/* lc: length of the candidate list the slow path of this panel worked from (0: none / fast path) */
+__device__ __forceinline__ PanelGeo panel_geo(const Mat &M, uint4 hd, unsigned lc, int w, int G, int b) {
+	PanelGeo g;
+	g.r1 = (long long)hd.y;
+	g.pm = ((u64)hd.w << 32) | hd.z;
+	/* sparse / rank-deficient mode: a panel whose pivots did NOT all come from its first 1024 rows
+	 * is followed by one that most likely needs all rows too -- the look-ahead search (one CTA busy,
+	 * and everybody's wait for its verdict) is skipped and the panel goes straight to the
+	 * candidate list.  A panel settled from its first rows switches the look-ahead back on. */
+	g.try_window = (hd.x >> 31) != 0;
+	/* Sparse sweep: when the slow path worked from a candidate list (the rows whose word of THIS
+	 * panel is non-zero) and that list is short, only the listed rows can have a non-zero
+	 * coefficient -- every strip but the one of the next panel word is swept over the list
+	 * instead of over all active rows (a unit of 1024 rows costs 8 KiB of coefficient reads even
+	 * when none of them has work: on MT19937 that was 20 us of a 44 us panel).  Row moves of the
+	 * panel are harmless: moved rows land on listed positions, and the coefficient is re-read. */
+	g.sparse_chunks = 0;
+	if (lc > 0 && (long long)lc * 4 <= M.m - g.r1) {
+		g.sparse_chunks = ((long long)lc + SWEEP_RU - 1) / SWEEP_RU;
+		g.try_window = false;
+	}
+	const int wn = w + 1;
+	g.s0 = wn >> SW_SHIFT;
+	g.base8 = g.r1 & ~7LL; /* chunks start on 512-byte boundaries of the strip */
+	g.nchunks = (M.m - g.base8 + SWEEP_RU - 1) / SWEEP_RU;
+	/* chunks per strip: the strip of the next panel word always takes every active row (it hands
+	 * pc_next and the next candidate list over); the others take the list in sparse mode */
+	const long long units = g.nchunks + (long long)(M.ns - g.s0 - 1) * (g.sparse_chunks ? g.sparse_chunks : g.nchunks);
+	/* the CTA that owns unit 0 runs the look-ahead search with every other warp of its SM idle and
+	 * restarts without a prefetched tile: it is dealt PERSIST_SEL_PAD fewer units */
+	const long long vpad = (wn < M.nw && g.try_window) ? max(0LL, min((long long)PERSIST_SEL_PAD, units / G - 1)) : 0;
+	const long long vunits = units + vpad;
+	g.u0 = max(0LL, vunits * b / G - vpad);
+	/* sparse mode: units [0, nchunks) are the rows of strip s0 (streaming loop); the list units that
+	 * follow are dealt out separately */
+	g.u1 = g.sparse_chunks ? min(vunits * (b + 1) / G, g.nchunks) : vunits * (b + 1) / G - vpad;
+	return g;
+}
+
+#ifndef GF2_EMU
+__device__ __forceinline__ uint4 ld_volatile_u4(const uint4 *p) {
+	uint4 v;
+	asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+	return v;
+}
+#else
+__device__ __forceinline__ uint4 ld_volatile_u4(const uint4 *p) {
+	const volatile unsigned *q = reinterpret_cast<const volatile unsigned *>(p);
+	return make_uint4(q[0], q[1], q[2], q[3]);
+}
+#endif
+
 #define PERSIST_CTRL_BYTES 64
 #define PERSIST_SMEM (SWEEP_LINES * 128 + SWEEP_SCRATCH_BYTES + 16 + PERSIST_CTRL_BYTES)
 static_assert(sizeof(ApplySmem) <= SWEEP_LINES * 128, "the apply scratch aliases the (dead) tables");
@@ -518,7 +585,6 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 	for (int w = w_begin; w < w_end; ++w) {
 		u64 *pc_cur = (w & 1) ? pc1 : pc0, *pc_next = (w & 1) ? pc0 : pc1;
 		const uint4 *ebuf = (w & 1) ? ebuf1 : ebuf0;
-		uint4 *ebuf_next = (w & 1) ? ebuf0 : ebuf1;
 		PanelDesc *pd = pd2 + (w & 1), *pdn = pd2 + ((w + 1) & 1);
 		if (blockIdx.x == 0 && tid == 0) t_panel[w] = gtimer_ns();
 		TRACE(0);
@@ -574,28 +640,9 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 		/* collect candidates for the next panel while sweeping a panel that needed the slow path */
 		const bool collect = slow;
 		list_ready = false;
-		/* sparse / rank-deficient mode: a panel whose pivots did NOT all come from its first 1024 rows
-		 * is followed by one that most likely needs all rows too -- the look-ahead search (17 us of one
-		 * CTA, and everybody's wait for its verdict) is skipped and the panel goes straight to the
-		 * candidate list.  A panel settled from its first rows switches the look-ahead back on. */
-		const long long r1 = (long long)hd.y;
-		/* Sparse sweep: when the slow path worked from a candidate list (the rows whose word of THIS
-		 * panel is non-zero) and that list is short, only the listed rows can have a non-zero
-		 * coefficient -- every strip but the one of the next panel word is swept over the list
-		 * instead of over all active rows (a unit of 1024 rows costs 8 KiB of coefficient reads even
-		 * when none of them has work: on MT19937 that was 20 us of a 44 us panel).  Row moves of the
-		 * panel are harmless: moved rows land on listed positions, and the coefficient is re-read.
-		 * The decision is taken here and again after the streaming loop (from the same words in
-		 * global memory) so that nothing of it stays live in registers across that loop. */
-		bool try_window = (hd.x >> 31) != 0;
-		long long sparse_chunks = 0; /* list chunks per strip in sparse mode, else 0 */
-		if (slow) {
-			const unsigned lc = __ldcg(&gs->list_cnt[w & 1]);
-			if (lc > 0 && (long long)lc * 4 <= m - r1) {
-				sparse_chunks = ((long long)lc + SWEEP_RU - 1) / SWEEP_RU;
-				try_window = false;
-			}
-		}
+		const PanelGeo geo = panel_geo(M, hd, slow ? __ldcg(&gs->list_cnt[w & 1]) : 0u, w, G, (int)blockIdx.x);
+		const long long r1 = geo.r1;
+		const bool try_window = geo.try_window;
 
 		const u64 pm = ((u64)hd.w << 32) | hd.z;
 		const int k = __popcll(pm);
@@ -619,21 +666,11 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 		}
 
 		/* ---- sweep(w): rows [r1, m) x strips [s0, ns) ---------------------------- */
-		const int s0 = wn >> SW_SHIFT;
-		const long long base8 = r1 & ~7LL; /* chunks start on 512-byte boundaries of the strip */
-		const long long nchunks = (m - base8 + SWEEP_RU - 1) / SWEEP_RU;
-		/* chunks per strip: the strip of the next panel word always takes every active row (it hands
-		 * pc_next and the next candidate list over); the others take the list in sparse mode */
-		const long long units = nchunks + (long long)(M.ns - s0 - 1) * (sparse_chunks ? sparse_chunks : nchunks);
-		/* the CTA that owns unit 0 runs the look-ahead search (~17 us with every other warp of its SM
-		 * idle) and restarts without a prefetched tile: it is dealt PERSIST_SEL_PAD fewer units
-		 * (A/B at n = 131072, profiles/r02_ab.md: 6: 609.7, 10: 605.4, 12: 604.6, 14: 604.2, 16: 604.7 ms) */
-		const long long vpad = (has_next && try_window) ? max(0LL, min((long long)PERSIST_SEL_PAD, units / G - 1)) : 0;
-		const long long vunits = units + vpad;
-		const long long u0 = max(0LL, vunits * blockIdx.x / G - vpad);
-		/* sparse mode: units [0, nchunks) are the rows of strip s0 (streaming loop); the list units that follow
-		 * are dealt with after it */
-		const long long u1 = sparse_chunks ? min(vunits * (blockIdx.x + 1) / G, nchunks) : vunits * (blockIdx.x + 1) / G - vpad;
+		const int s0 = geo.s0;
+		/* 32-bit counters inside the streaming loop (units of a panel = strips x chunks < 2^31 for any
+		 * matrix that fits a GPU): every 64-bit value kept across the loop costs it two registers */
+		const long long base8 = geo.base8;
+		const int nchunks = (int)geo.nchunks, u0 = (int)geo.u0, u1 = (int)geo.u1;
 		const int nch = (wn & (SW - 1)) >> 1;
 		u64 colmask_next = ~0ULL;
 		if (wn == nw - 1 && (M.n & 63)) colmask_next = (1ULL << (M.n & 63)) - 1;
@@ -648,13 +685,13 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 #if SWEEP_LEAN_UNITS
 			const smem_addr_t te32 = smem_addr(Tbe), to32 = smem_addr(Tbo);
 			/* chunks [lean_lo, lean_hi) of a strip other than s0 lie entirely inside the active rows */
-			const long long lean_lo = (base8 >= r1) ? 0 : 1, lean_hi = (m - base8) / SWEEP_RU;
+			const int lean_lo = (base8 >= r1) ? 0 : 1, lean_hi = (int)((m - base8) / SWEEP_RU);
 #endif
 			int cur = -1, fetched = -1;
 			const int s_last = s0 + (int)((u1 - 1) / nchunks);
 			int s = s0 + (int)(u0 / nchunks);
-			long long chunk = u0 % nchunks; /* (strip, row chunk) of unit u, advanced without dividing */
-			for (long long u = u0; u < u1; ++u, ++chunk) {
+			int chunk = u0 % nchunks; /* (strip, row chunk) of unit u, advanced without dividing */
+			for (int u = u0; u < u1; ++u, ++chunk) {
 				if (chunk == nchunks) {
 					chunk = 0;
 					++s;
@@ -683,17 +720,17 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 					if (cur < 0) TRACE(1); /* first tables of the panel built */
 					cur = s;
 				}
-				const long long row0 = base8 + chunk * SWEEP_RU + rl;
+				const long long row0 = base8 + (long long)chunk * SWEEP_RU + rl;
 				const bool force = (s == s0);
 				uint4 *p = mb + ((long long)s * M.mp + row0) * SQ + ch;
 #if SWEEP_LEAN_UNITS
 				if (!force && chunk >= lean_lo && chunk < lean_hi) {
 					/* every consecutive lean unit of this strip in one tight loop (few live values: the
 					 * per-thread constants stay in registers instead of being re-derived per row piece) */
-					const long long nl = min(lean_hi - chunk, u1 - u);
+					const int nl = min(lean_hi - chunk, u1 - u);
 					const u64 *pcp = pc_cur + row0;
 #pragma unroll 1
-					for (long long i = 0; i < nl; i++, p += (long long)SWEEP_RU * SQ, pcp += SWEEP_RU)
+					for (int i = 0; i < nl; i++, p += (long long)SWEEP_RU * SQ, pcp += SWEEP_RU)
 						lean_unit(p, pcp, pm, te32, to32, bsel);
 					u += nl - 1;
 					chunk += nl - 1;
@@ -806,41 +843,46 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 			}
 		}
 
-		if (slow) {
-			/* sparse mode (decided as at the top of the panel): this CTA's share of the list units */
-			const unsigned lc = *(volatile unsigned *)&gs->list_cnt[w & 1];
-			if (lc > 0 && (long long)lc * 4 <= m - r1) {
-				const long long oc = ((long long)lc + SWEEP_RU - 1) / SWEEP_RU;
-				const long long all = nchunks + (long long)(M.ns - s0 - 1) * oc;
-				const long long a0 = max(all * blockIdx.x / G, nchunks), a1 = all * (blockIdx.x + 1) / G;
-				if (a0 < a1)
-					phase = sparse_sweep(mb, M.mp, TD, P, E, bar, phase, ebuf, cand + (size_t)(w & 1) * PERSIST_CAND_MAX * 2, lc,
-					                     a0 - nchunks, a1 - nchunks, oc, s0 + 1, r1, pc_cur, pm);
-			}
+		/* ---- after the streaming loop: the panel's geometry is derived AGAIN, from re-read words
+		 * (see PanelGeo), so that the loop above shares no registers with what follows -------- */
+		const uint4 hd2 = ld_volatile_u4(&gs->hdr[w & 1]);
+		const unsigned lc2 = slow ? *(volatile unsigned *)&gs->list_cnt[w & 1] : 0u;
+		const PanelGeo g2 = panel_geo(M, hd2, lc2, w, G, (int)blockIdx.x);
+		const int wn2 = w + 1;
+		const bool has_next2 = wn2 < M.nw;
+		if (g2.sparse_chunks) {
+			/* sparse mode: this CTA's share of the list units */
+			const long long all = g2.nchunks + (long long)(M.ns - g2.s0 - 1) * g2.sparse_chunks;
+			const long long a0 = max(all * blockIdx.x / G, g2.nchunks), a1 = all * (blockIdx.x + 1) / G;
+			if (a0 < a1)
+				phase = sparse_sweep(mb, M.mp, TD, P, E, bar, phase, ebuf, cand + (size_t)(w & 1) * PERSIST_CAND_MAX * 2, lc2,
+				                     a0 - g2.nchunks, a1 - g2.nchunks, g2.sparse_chunks, g2.s0 + 1, g2.r1, pc_cur, g2.pm);
 		}
 
-		list_ready = collect && has_next;
+		list_ready = slow && has_next2; /* candidates for the next panel were collected while this one was swept */
 		/* ---- apply(w+1) for the strips whose first-rows unit this CTA swept ------- */
 		TRACE(2); /* my units are done */
-		if (has_next) {
+		if (has_next2) {
 			__syncthreads(); /* the tables are dead: their space is the apply scratch */
 			if (tid == 0) {
 				/* 1: the look-ahead settled the next panel, 2: it could not (or did not run: slow path), 0: fault.
 				 * The acquire load that saw the flag orders this thread; the CTA barrier below hands that
 				 * order on to the threads that read the description (ld.cg: never a stale L1 line) */
-				*s_state = try_window ? persist_wait(&gs->sel_flag, (unsigned)wn + 1, &gs->need_full, gs) : 2;
+				*s_state = g2.try_window ? persist_wait(&gs->sel_flag, (unsigned)wn2 + 1, &gs->need_full, gs) : 2;
 			}
 			__syncthreads();
 			const int state = *s_state;
 			if (state == 0) return;
 			TRACE(3); /* the next panel's description is there */
-			if (state == 1 && u0 < u1) {
-				const long long sa = (u0 + nchunks - 1) / nchunks, sb = (u1 - 1) / nchunks; /* strips (relative) whose chunk 0 is mine */
+			if (state == 1 && g2.u0 < g2.u1) {
+				/* strips (relative) whose chunk 0 is mine */
+				const long long sa = (g2.u0 + g2.nchunks - 1) / g2.nchunks, sb = (g2.u1 - 1) / g2.nchunks;
 				const int cnt = (int)(sb - sa + 1);
-				persist_apply(M, pdn, ebuf_next, AP, cnt > 0 ? cnt : 0, [&](int i) { return s0 + (int)sa + i; });
+				const int sfirst = g2.s0 + (int)sa;
+				persist_apply(M, pd2 + (wn2 & 1), (w & 1) ? ebuf0 : ebuf1, AP, cnt > 0 ? cnt : 0, [&](int i) { return sfirst + i; });
 			}
 		}
-		if (blockIdx.x == 0 && tid == 0) gs->done_w = wn;
+		if (blockIdx.x == 0 && tid == 0) gs->done_w = wn2;
 		TRACE(4); /* apply done */
 		if (!grid_barrier(gs, s_ok)) return;
 		TRACE(5);
