@@ -758,19 +758,17 @@ static_assert(SWEEP_THREADS == 8 * 32 * 4, "one partial-table item per thread; (
 
 #if SW == 8
 /* ---- the lean streaming unit (64-byte strips) -------------------------------------------
- * ncu on the first k_forward (profiles/r02r_forward_ncu.md): besides l1tex (the lookups) and HBM
- * the ALU pipe is a co-limiter of the streaming loop -- 450 SASS instructions per unit and
- * thread where the arithmetic needs ~220: row-range predicates, the look-ahead / candidate-list
- * branches and, per lookup, the generic-to-shared address conversion the compiler re-derives
- * when registers are short (S2R CgaCtaId + LEA).  Units that lie entirely inside the active rows
- * of a strip other than the next panel word's -- all but a few hundred of the 32768 units of a
- * large panel -- take this path instead: no predicates, 32-bit shared-memory addresses computed
- * once per thread, one byte extract (ALU) + one multiply-add (FMA pipe) per lookup: 275 instructions
- * per unit, 651 -> 620 ms at n = 131072 on one box (profiles/r02_ab.md, calls S and T).  Measured and
- * dropped there: the same loop behind a call boundary (221 instructions but 642 ms), all eight loads
- * of a unit issued before the first lookup (691 ms: ptxas' own schedule, which requests row piece
- * q + 2 while piece q is looked up, is the better one), a rolling pipeline that requests unit i + 1
- * piece by piece (731 ms) and a TMA bulk prefetch of the next units into L2 (650 - 670 ms). */
+ * Units that lie entirely inside the active rows of a strip other than the next panel word's --
+ * all but a few hundred of the 32768 units of a large panel -- take this path instead of the
+ * general one: no row-range predicates, 32-bit shared-memory addresses computed once per
+ * thread, per lookup one byte extract (PRMT, ALU) + one multiply-add (IMAD, FMA pipe) + LDS.128.
+ * ncu (profiles/r02z_sweep_ncu.md against r01g): 426 M -> 235 M instructions per launch, issue
+ * slots 53 % -> 30 % busy, and the SAME duration -- the loop is bound by the bytes it moves through
+ * the l1tex data pipe (88 %), not by what it executes; the lean form is kept for the halved
+ * instruction stream.  Measured and dropped on the way (profiles/r02_ab.md
+ * calls S - T): the loop behind a call boundary, all eight loads of a unit issued before the first
+ * lookup (ptxas' own schedule, which requests row piece q + 2 while piece q is looked up, is the
+ * better one), a rolling pipeline over units, a TMA bulk prefetch of the next units into L2. */
 #ifndef SWEEP_LEAN_UNITS
 #define SWEEP_LEAN_UNITS 1
 #endif

@@ -487,10 +487,9 @@ __device__ __noinline__ unsigned sparse_sweep(uint4 *mb, long long mp, uint4 *TD
 /* What a CTA derives from the header of a panel: its share [u0, u1) of the panel's work units and
  * the geometry behind it.  Computed before the streaming loop and AGAIN after it, from words
  * re-read from global memory: written once and used on both sides of the loop, these values
- * stayed in registers across it, and ptxas paid for them inside the loop -- it re-derived the
- * per-thread constants for every row piece and staggered the coefficient loads (275 instructions
- * per lean unit where k_sweep, with the same source, needs 229: the launch chain had become
- * faster than the persistent kernel at n = 131072, 606 against 622 ms, profiles/r02_ab.md call U). */
+ * stayed in registers across it, and ptxas paid for them inside the loop (it re-derived the
+ * per-thread constants for every row piece: 275 instructions per lean unit, 233 without; an
+ * intermediate build with more such state ran the whole solve 6 % slower). */
 struct PanelGeo {
 	long long r1, base8, nchunks, u0, u1;
 	long long sparse_chunks; /* list chunks per strip in sparse mode, else 0 */
