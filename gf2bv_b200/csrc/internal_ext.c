@@ -24,6 +24,7 @@
 
 #include <dlfcn.h>
 #include <pthread.h>
+#include <unistd.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -214,9 +215,66 @@ static uint64_t *stage_reserve(slot_t *sl, size_t bytes) {
 /* Equation int -> one matrix row.  Bit 0 is the constant term (returned), bit k
  * (1..cols) is the coefficient of unknown k-1 and lands at row bit k-1; higher
  * bits are dropped and the sign is ignored (digits are the magnitude), exactly
- * what the reference's bit walk does (:41-59, :411-425).  Streams the 30-bit
- * digits through a 128-bit accumulator and writes every word of the row exactly
- * once (the staging buffer needs no clearing). */
+ * what the reference's bit walk does (:41-59, :411-425). */
+#if PyLong_SHIFT == 30
+/* 32 digits of 30 bits are exactly 15 words: with the loop fully unrolled every shift is a
+ * constant (about three operations per digit where a running 128-bit accumulator needed ~25
+ * cycles), and a block of zero digits -- almost all of them on MT19937-class systems -- is
+ * recognised with one OR-reduction. */
+static inline void digits32_to_words15(const digit *d, uint64_t *V) {
+	uint64_t any = 0;
+#pragma GCC unroll 32
+	for (int i = 0; i < 32; i++) any |= d[i];
+	if (!any) {
+		memset(V, 0, 15 * 8);
+		return;
+	}
+	uint64_t w[16] = {0};
+#pragma GCC unroll 32
+	for (int i = 0; i < 32; i++) {
+		const int bit = 30 * i, j = bit >> 6, sh = bit & 63;
+		const uint64_t x = d[i];
+		w[j] |= x << sh;
+		if (sh > 34) w[j + 1] |= x >> (64 - sh);
+	}
+	memcpy(V, w, 15 * 8);
+}
+
+static inline int pack_equation(PyObject *eq, uint64_t *row, int64_t nw, int64_t cols) {
+	Py_ssize_t nd = LONG_NDIGITS(eq);
+	if (nd == 0) {
+		memset(row, 0, (size_t)nw * 8);
+		return 0;
+	}
+	const digit *d = LONG_DIGITS(eq);
+	const int cbit = (int)(d[0] & 1);
+	/* only the digits that reach bits 0..cols of the int */
+	const Py_ssize_t need = ((Py_ssize_t)cols + 1 + 29) / 30;
+	if (nd > need) nd = need;
+	/* V = the int's bits as 64-bit words: words 0..nw-1 go to row[], word nw (bit `cols` can sit there) to top */
+	uint64_t top = 0;
+	Py_ssize_t i = 0;
+	int64_t w = 0;
+	for (; i + 32 <= nd && w + 15 <= nw; i += 32, w += 15) digits32_to_words15(d + i, row + w);
+	if (w < nw) memset(row + w, 0, (size_t)(nw - w) * 8);
+	for (; i < nd; i++) {
+		const int64_t bit = 30 * (int64_t)i, j = bit >> 6;
+		const int sh = (int)(bit & 63);
+		const uint64_t x = d[i];
+		if (j < nw) row[j] |= x << sh;
+		else if (j == nw) top |= x << sh;
+		if (sh > 34) {
+			if (j + 1 < nw) row[j + 1] |= x >> (64 - sh);
+			else if (j + 1 == nw) top |= x >> (64 - sh);
+		}
+	}
+	/* row = V >> 1 (bit 0 was the constant term) */
+	for (int64_t j = 0; j + 1 < nw; j++) row[j] = (row[j] >> 1) | (row[j + 1] << 63);
+	row[nw - 1] = (row[nw - 1] >> 1) | (top << 63);
+	if (cols & 63) row[nw - 1] &= (1ULL << (cols & 63)) - 1;
+	return cbit;
+}
+#else
 static inline int pack_equation(PyObject *eq, uint64_t *row, int64_t nw, int64_t cols) {
 	const Py_ssize_t nd = LONG_NDIGITS(eq);
 	if (nd == 0) {
@@ -246,6 +304,7 @@ static inline int pack_equation(PyObject *eq, uint64_t *row, int64_t nw, int64_t
 	if (cols & 63) row[nw - 1] &= (1ULL << (cols & 63)) - 1;
 	return cbit;
 }
+#endif
 
 /* All equations -> A (rows x nw words) and b (rows bits).  Large systems are packed
  * by several threads WITHOUT the GIL: the caller's list items are pinned by strong
@@ -296,9 +355,9 @@ static void *pack_worker(void *arg) {
 	return NULL;
 }
 
-#define PACK_MAX_THREADS 8
-#define PACK_MIN_WORDS_PER_THREAD (1 << 20)
-#define PACK_BLOCK_BYTES (4u << 20)
+#define PACK_MAX_THREADS 16
+#define PACK_MIN_WORDS_PER_THREAD (1 << 19)
+#define PACK_BLOCK_BYTES (2u << 20)
 
 /* does a system of this size take the multi-threaded, streaming path? */
 static int pack_threads(Py_ssize_t rows, int64_t nw) {
@@ -306,6 +365,9 @@ static int pack_threads(Py_ssize_t rows, int64_t nw) {
 	const char *env = getenv("GF2B200_PACK_MIN_WORDS"); /* tests: take the streaming path on small systems */
 	if (env && atoll(env) > 0) minw = atoll(env);
 	int64_t n = ((int64_t)rows * nw) / minw;
+	/* never more workers than cores (one core stays with the thread that feeds the GPU) */
+	const long cores = sysconf(_SC_NPROCESSORS_ONLN);
+	if (cores > 1 && n > cores - 1) n = cores - 1;
 	return n > PACK_MAX_THREADS ? PACK_MAX_THREADS : (int)n;
 }
 
