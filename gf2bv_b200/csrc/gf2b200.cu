@@ -54,7 +54,8 @@ struct gf2b200_ctx {
 	int profile;
 	int rank, world; /* shard index of the first local shard, number of shards */
 	int n_local;     /* local shards: 1 (single, nccl) or world (loopback) */
-	int persist;     /* the one-kernel forward elimination (k_forward) can be launched cooperatively */
+	int coop;        /* a grid of n_sm CTAs of SWEEP_THREADS threads can be launched cooperatively (k_forward, k_sweep_apply) */
+	int persist;     /* k_forward: 0 never, 1 for matrices below PERSIST_AUTO_BYTES, 2 always (GF2B200_FORWARD) */
 	ncclComm_t nccl; /* nccl contexts */
 	struct gf2b200_system *cached; /* device buffers of the last gf2b200_solve, reused for equal shapes */
 	/* host-buffer loads: staging buffers, copy stream and events live as long as the context
@@ -215,6 +216,7 @@ static int ctx_init(gf2b200_ctx **out, int device) {
 	/* the one-kernel forward elimination needs every CTA of a grid of n_sm resident at once
 	 * (cooperative launch); GF2B200_FORWARD=launches keeps the per-panel launch chain */
 	if (e == cudaSuccess) e = cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, PERSIST_SMEM);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM);
 	if (e == cudaSuccess) {
 		/* 1: k_forward for systems below PERSIST_AUTO_BYTES (default), 2: always (GF2B200_FORWARD=persist),
 		 * 0: never (GF2B200_FORWARD=launches) */
@@ -226,8 +228,11 @@ static int ctx_init(gf2b200_ctx **out, int device) {
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_forward, SWEEP_THREADS, PERSIST_SMEM) != cudaSuccess)
 			per_sm = 0;
 		cudaGetLastError();
-		if (!coop || per_sm < 1) c->persist = 0;
+		c->coop = coop && per_sm >= 1;
+#else
+		c->coop = 1;
 #endif
+		if (!c->coop) c->persist = 0;
 	}
 #endif
 	if (e != cudaSuccess) {
@@ -504,7 +509,7 @@ extern "C" int gf2b200_system_create(gf2b200_ctx *ctx, int64_t m, int64_t n, gf2
 		h.d_ebuf2 = nullptr; h.d_gs = nullptr; h.d_tpanel = nullptr; h.d_cand = nullptr;
 		h.xch = nullptr; h.d_pt = nullptr;
 		h.d_x = h.d_slab = h.d_slab_all = nullptr;
-		e = shard_alloc(h, ctx->world, ctx->persist != 0);
+		e = shard_alloc(h, ctx->world, ctx->coop != 0);
 	}
 	if (e != cudaSuccess) {
 		int rc = fail(ctx, e == cudaErrorMemoryAllocation ? GF2B200_ENOMEM : GF2B200_ECUDA,
@@ -748,6 +753,10 @@ static int forward_single(gf2b200_system *sys, long long *launches) {
 	(*launches)++;
 	const int apply_cap = ctx->n_sm * APPLY_CTAS_PER_SM;
 	const bool fused = !getenv("GF2B200_NO_FUSED_SELECT"); /* diagnostic switch */
+#if SW == 8
+	/* needs the second E-tile buffer and a cooperative launch (both there when k_forward is possible) */
+	const bool tail_apply = fused && ctx->coop && h.d_ebuf2 && !getenv("GF2B200_NO_TAIL_APPLY");
+#endif
 	for (int w = 0; w < nw; w++) {
 		u64 colmask = ~0ULL;
 		if (w == nw - 1 && (M.n & 63)) colmask = (1ULL << (M.n & 63)) - 1;
@@ -762,6 +771,25 @@ static int forward_single(gf2b200_system *sys, long long *launches) {
 			(*launches)++;
 		}
 		int s0a = w >> SW_SHIFT;
+#if SW == 8
+		if (tail_apply) {
+			/* k_sweep_apply: the sweep of panel w applies panel w + 1 in its tail (into the other E-tile
+			 * buffer); k_apply is then a no-op, as k_select is after a successful look-ahead */
+			uint4 *eb = (w & 1) ? h.d_ebuf2 : h.d_ebuf, *eb_next = (w & 1) ? h.d_ebuf : h.d_ebuf2;
+			k_apply<<<std::min(M.ns - s0a, apply_cap), APPLY_THREADS, 0, st>>>(M, pd, eb, s0a);
+			if (prof) CK(ctx, cudaEventRecord(sys->ev[6 + 2 * w], st));
+			cudaLaunchAttribute at[1];
+			at[0].id = cudaLaunchAttributeCooperative;
+			at[0].val.cooperative = 1;
+			cudaLaunchConfig_t cfg = {dim3(ctx->n_sm), dim3(SWEEP_THREADS), SWEEP_SMEM, st, at, 1};
+			CK(ctx, cudaLaunchKernelEx(&cfg, k_sweep_apply, M, (const PanelDesc *)pd, (const u64 *)pc_cur, pc_next,
+			                           (const uint4 *)eb, eb_next, w, (w + 1) >> SW_SHIFT, pdn, h.d_state, h.d_hist_r,
+			                           h.d_hist_pm, colmask_next));
+			if (prof) CK(ctx, cudaEventRecord(sys->ev[7 + 2 * w], st));
+			*launches += 2;
+			continue;
+		}
+#endif
 		k_apply<<<std::min(M.ns - s0a, apply_cap), APPLY_THREADS, 0, st>>>(M, pd, h.d_ebuf, s0a);
 		if (prof) CK(ctx, cudaEventRecord(sys->ev[6 + 2 * w], st));
 		k_sweep<<<ctx->n_sm, SWEEP_THREADS, SWEEP_SMEM, st>>>(M, pd, pc_cur, pc_next, h.d_ebuf, w,

@@ -81,12 +81,15 @@ struct PanelDesc {
 	int k;           /* pivots found in this panel */
 	int nmove;       /* displaced rows to relocate */
 	int valid;       /* panel index + 1 this description belongs to (0: none) */
-	int pad;
+	int applied;     /* panel index + 1 if the sweep that settled this panel also applies it in its tail
+	                  * (k_sweep_apply: k_apply is then a no-op); 0 otherwise */
 	u64 pm;          /* pivot column mask within the panel word */
 	u64 TB[64];      /* by column c: combination of selected rows giving E_c; 0 if c is free */
 	int sel[64];     /* physical row of the l-th selected row */
 	int mv_src[64];
 	int mv_dst[64];
+	unsigned look;   /* panel index + 1 once the look-ahead search of the previous sweep has decided (valid or not) */
+	int pad2;
 };
 
 struct SolverState {
@@ -481,6 +484,7 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
 	__shared__ int ssel[64], ssrc[64], sdst[64];
 	const int k = pd->k;
 	if (k == 0) return;
+	if (pd->applied != 0 && pd->applied == pd->valid) return; /* the previous sweep's tail applied this panel */
 	const int tid = threadIdx.x, rr = tid / SQ, ch = tid % SQ;
 	const long long r = pd->r;
 	const int nmove = pd->nmove;
@@ -756,6 +760,21 @@ static_assert(SWEEP_THREADS == 8 * 32 * 4, "one partial-table item per thread; (
 #define SWEEP_TAIL_SELECT 0
 #endif
 
+/* gpu-scope release / acquire of a flag word (look-ahead verdicts inside a launch, k_forward's barriers) */
+#ifndef GF2_EMU
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+	unsigned v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+#else
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#endif
+
 #if SW == 8
 /* ---- the lean streaming unit (64-byte strips) -------------------------------------------
  * Units that lie entirely inside the active rows of a strip other than the next panel word's --
@@ -848,7 +867,7 @@ __device__ __forceinline__ void
 sweep_body(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
            u64 *__restrict__ pc_next, const uint4 *__restrict__ ebuf, int w, int s0,
            PanelDesc *pd_next, SolverState *st, long long *hist_r, u64 *hist_pm, u64 colmask_next,
-           const DistLook *dl = nullptr) {
+           const DistLook *dl = nullptr, bool publish_look = false) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint4 *TD = reinterpret_cast<uint4 *>(smem_raw);
 #if SW == 16
@@ -1064,10 +1083,21 @@ sweep_body(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_c
 				 * process per GPU) the global election runs here too, while the sweep goes on */
 				dist_lookahead(dl, S, pc_next, wn, colmask_next, r1, lim, m, st, pd_next, hist_r, hist_pm);
 			} else if (tid < 32) {
-				if (S.pm == colmask_next || lim == m)
+				const bool final_ = (S.pm == colmask_next || lim == m);
+				if (final_)
 					select_finalize(S, pc_next, wn, r1, st, pd_next, hist_r, hist_pm);
 				else if (tid == 0)
 					pd_next->valid = 0;
+				if (publish_look) {
+					/* k_sweep_apply: the other CTAs wait for this verdict in their tails and, when it is
+					 * "valid", apply the next panel themselves */
+					__syncwarp();
+					if (tid == 0) {
+						pd_next->applied = final_ ? wn + 1 : 0;
+						__threadfence();
+						st_release_gpu(&pd_next->look, (unsigned)wn + 1);
+					}
+				}
 			}
 			__syncthreads();
 		}

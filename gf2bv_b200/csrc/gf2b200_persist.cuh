@@ -117,14 +117,6 @@ __device__ __forceinline__ void hdr_publish(GridSync *gs, int w, long long r1, u
 #endif
 
 #ifndef GF2_EMU
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
-	unsigned v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
-	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ unsigned long long gtimer_ns() {
 	unsigned long long t;
 	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -134,8 +126,6 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
  * before the async-proxy read of the bulk copy that follows */
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 #else
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
-__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 __device__ __forceinline__ unsigned long long gtimer_ns() { return (unsigned long long)(emu_now_ms() * 1e6); }
 __device__ __forceinline__ void fence_proxy_async() {}
 #endif
@@ -887,6 +877,59 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 		TRACE(5);
 	}
 	if (blockIdx.x == 0 && tid == 0) t_panel[w_end] = gtimer_ns();
+}
+
+
+/* ---- k_sweep_apply: the launch chain's sweep with the NEXT panel's apply in its tail ------------
+ * The launch chain (k_select -> k_apply -> k_sweep per panel) streams faster than k_forward on large
+ * matrices but pays ~16 us per panel outside the sweep (k_apply 7.8 us, a no-op k_select 2.7 us,
+ * gaps: profiles/r02y_launches.md).  This kernel is k_sweep plus what k_forward does after its
+ * streaming loop: a CTA that has swept its units waits for the verdict of the look-ahead search
+ * (PanelDesc::look, released by the CTA that ran it inside sweep_body) and, when the next panel is
+ * settled, builds E = TB * Sel for the strips whose first-rows unit IT swept -- rows nobody else
+ * touches in this launch -- into the OTHER E-tile buffer.  k_apply of the next panel then returns at
+ * once (PanelDesc::applied).  Launched cooperatively: the waits need every CTA resident. */
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+k_sweep_apply(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur, u64 *__restrict__ pc_next,
+              const uint4 *__restrict__ ebuf, uint4 *__restrict__ ebuf_next, int w, int s0, PanelDesc *pd_next,
+              SolverState *st, long long *hist_r, u64 *hist_pm, u64 colmask_next) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	sweep_body(M, pd, pc_cur, pc_next, ebuf, w, s0, pd_next, st, hist_r, hist_pm, colmask_next, nullptr, true);
+	if (!pd_next) return;
+	/* this CTA's share of the units, as sweep_body dealt them */
+	const int k = pd->k;
+	const long long r1 = pd->r1, m = M.m;
+	if (r1 >= m || k == 0) return; /* no sweep, no look-ahead: k_select / k_apply settle the next panel */
+	const long long nchunks = (m - r1 + SWEEP_RU - 1) / SWEEP_RU;
+	const long long units = (long long)(M.ns - s0) * nchunks;
+	const long long vpad = max(0LL, min((long long)SWEEP_SEL_PAD, units / gridDim.x - 1));
+	const long long vunits = units + vpad;
+	const long long u0 = max(0LL, vunits * blockIdx.x / gridDim.x - vpad);
+	const long long u1 = vunits * (blockIdx.x + 1) / gridDim.x - vpad;
+	if (u0 >= u1) return;
+	const long long sa = (u0 + nchunks - 1) / nchunks, sb = (u1 - 1) / nchunks; /* strips (relative) whose chunk 0 is mine */
+	if (sa > sb) return;
+	__shared__ int s_verdict;
+	__syncthreads(); /* the tables are dead: their space is the apply scratch */
+	if (threadIdx.x == 0) {
+		const unsigned long long t0 = gtimer_ns();
+		int v = -1;
+		unsigned it = 0;
+		while (ld_acquire_gpu(&pd_next->look) != (unsigned)w + 2) {
+			if ((++it & 63) == 0 && gtimer_ns() - t0 > PERSIST_TIMEOUT_NS) {
+				v = 0; /* (cannot happen with every CTA resident; k_apply would then redo the panel -- see applied) */
+				break;
+			}
+			__nanosleep(40);
+		}
+		if (v < 0) v = (*(volatile int *)&pd_next->valid == w + 2) ? 1 : 0;
+		s_verdict = v;
+	}
+	__syncthreads();
+	if (!s_verdict) return;
+	ApplySmem &AP = *reinterpret_cast<ApplySmem *>(smem_raw);
+	const int sfirst = s0 + (int)sa;
+	persist_apply(M, pd_next, ebuf_next, AP, (int)(sb - sa + 1), [&](int i) { return sfirst + i; });
 }
 
 } /* namespace gf2b200 */

@@ -130,12 +130,10 @@ class LinearSystem:
         return mat, rhs
 
     def get_sage_mat(self, zeros: Zeros):
-        """Fast Sage conversion of the reference (via libgd); not provided here --
-        the helper raises RuntimeError, then we fall back to the slow conversion."""
-        try:
-            eqs_to_sage_mat_helper(self.get_eqs(zeros), self._cols)
-        except RuntimeError:
-            return self.get_sage_mat_slow(zeros)
+        """The reference converts through libgd (`eqs_to_sage_mat_helper`, reference
+        __init__.py:289-305); that bridge is out of scope here (the helper only raises
+        RuntimeError, as the reference's does without libgd), so this is the slow conversion."""
+        return self.get_sage_mat_slow(zeros)
 
 
 class QuadraticSystem(LinearSystem):
