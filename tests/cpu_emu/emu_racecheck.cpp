@@ -254,6 +254,11 @@ int __tsan_atomic32_fetch_add(volatile int *p, int v, int) {
 	atomic_rmw((uintptr_t)p);
 	return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
 }
+int __tsan_atomic32_exchange(volatile int *p, int v, int) {
+	access((uintptr_t)p, 4, true, true, PC);
+	atomic_rmw((uintptr_t)p);
+	return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST);
+}
 long long __tsan_atomic64_load(const volatile long long *p, int) {
 	access((uintptr_t)p, 8, false, true, PC);
 	return __atomic_load_n(p, __ATOMIC_SEQ_CST);

@@ -273,6 +273,13 @@ def test_forward_paths_agree(ctx):
         A, b = _rand_system(rnd, m, n, rank_cap=cap, consistent=True)
         g1, g2 = ctx.solve(A, b, n, 1), ctx2.solve(A, b, n, 1)
         _assert_same(g1, g2, 1)
+        # the chain without k_sweep_apply (the sweep's tail applying the next panel): plain k_apply + k_sweep
+        os.environ["GF2B200_NO_TAIL_APPLY"] = "1"
+        try:
+            g3 = ctx2.solve(A, b, n, 1)
+        finally:
+            del os.environ["GF2B200_NO_TAIL_APPLY"]
+        _assert_same(g1, g3, 1)
     n = 2048 if os.environ.get("GF2B200_TEST_EMULATION") == "1" else 16384
     outs = []
     for c in (ctx, ctx2):
