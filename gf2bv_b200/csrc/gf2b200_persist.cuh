@@ -184,10 +184,11 @@ __device__ __forceinline__ bool grid_barrier(GridSync *gs, int *s_ok) {
  * ~66 insertions per panel on the critical path of EVERY panel it was the longest link of
  * the chain for n <= 32768 and for the last quarter of the panels of any n. */
 __device__ __forceinline__ void window_search(SelectSmem &S, long long base8, u64 colmask, int lane) {
-	for (int c = lane; c < 64; c += 32) {
-		S.sel[c] = -1;
-		S.topsel[c] = 0;
-	}
+	for (int c = lane; c < 64; c += 32) S.topsel[c] = 0;
+	/* S.sel[] is initialised by the lane that fills it below (no write after another lane's write:
+	 * compute-sanitizer racecheck flagged the lane-parallel form) */
+	if (lane == 0)
+		for (int c = 0; c < 64; c++) S.sel[c] = -1;
 	u64 Clo = 0, Chi = 0, Tlo = 0, Thi = 0, pm = 0;
 	int nsel = 0;
 	for (int g = 0; g < SWEEP_RU / 32 && pm != colmask; g++) {
