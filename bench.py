@@ -275,7 +275,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     n_launch = 1 if one_kernel else max(1, stp["sweep_launches"])
     roofline = {
         "kernel": "k_forward (persistent: every panel's sweep + look-ahead pivot search + apply in ONE launch)"
-                  if one_kernel else "k_sweep",
+                  if one_kernel else ("k_sweep_dist" if world > 1 else
+                                      "k_sweep" if os.environ.get("GF2B200_NO_TAIL_APPLY") else
+                                      "k_sweep_apply (k_sweep + the next panel's apply in its tail; per-panel launch chain)"),
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic * stp["sweep_launches"] / n_launch if traffic else None,
         "traffic_note": traffic_note,
