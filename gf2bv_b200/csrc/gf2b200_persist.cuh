@@ -52,14 +52,20 @@ struct GridSync {
 	/* what every CTA needs at the top of a panel, in ONE 16-byte load: {valid = panel + 1,
 	 * r1 = first active row, pm lo, pm hi}; slot = panel & 1 (k = popcount(pm)) */
 	uint4 hdr[2];
+	/* the same header written by the SLOW path of a panel.  It must not go to hdr[]: every CTA decides
+	 * "slow or not" from hdr[panel & 1] at the top of the panel, and a CTA that gets there late -- after
+	 * CTA 0 has already published its verdict -- would read a valid header, skip the slow path's apply
+	 * and barrier, and leave the grid barriers out of step.  (Never seen at full speed, where CTA 0
+	 * needs microseconds and the others nanoseconds; compute-sanitizer's racecheck, which slows and
+	 * skews the CTAs, ran into it: profiles/r02_sanitizer.md.) */
+	uint4 hdr_slow;
 };
 
 /* bit 31 of the first word: "the rows selected for this panel all came from its first 1024 active
  * rows" -- the look-ahead of the next panel is worth trying (set by the look-ahead itself, and by the
  * slow path when a dense-looking panel follows a sparse one) */
-__device__ __forceinline__ void hdr_publish(GridSync *gs, int w, long long r1, u64 pm, bool window_ok) {
-	__stcg(&gs->hdr[w & 1], make_uint4((unsigned)(w + 1) | (window_ok ? 0x80000000u : 0u), (unsigned)r1, (unsigned)pm,
-	                                   (unsigned)(pm >> 32)));
+__device__ __forceinline__ void hdr_publish(uint4 *slot, int w, long long r1, u64 pm, bool window_ok) {
+	__stcg(slot, make_uint4((unsigned)(w + 1) | (window_ok ? 0x80000000u : 0u), (unsigned)r1, (unsigned)pm, (unsigned)(pm >> 32)));
 }
 
 /* How the sweep reads a row's coefficient (the panel word pc_cur[row]):
@@ -603,7 +609,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 					select_finalize(S, pc_cur, w, r, st, pd, hist_r, hist_pm);
 					__syncwarp();
 					if (tid == 0) {
-						hdr_publish(gs, w, r + S.nsel, S.pm, window_ok);
+						hdr_publish(&gs->hdr_slow, w, r + S.nsel, S.pm, window_ok);
 						gs->list_cnt[w & 1] = (cnt <= PERSIST_CAND_MAX) ? cnt : 0u;
 						__threadfence();
 						st_release_gpu(&gs->sel_flag, (unsigned)w + 1);
@@ -623,7 +629,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 			persist_apply(M, pd, const_cast<uint4 *>(ebuf), AP, mine > 0 ? mine : 0,
 			              [&](int i) { return s0a + (int)blockIdx.x + i * G; });
 			if (!grid_barrier(gs, s_ok)) return;
-			hd = __ldcg(&gs->hdr[w & 1]);
+			hd = __ldcg(&gs->hdr_slow);
 		}
 		/* the list of this panel is consumed (or was not needed); its slot is refilled two panels on */
 		if (blockIdx.x == 0 && tid == 0) gs->cand_cnt[w & 1] = 0;
@@ -822,7 +828,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 						__syncwarp();
 						TRACE_W0(0); /* (slot 0 re-used by the search CTA: finalize done) */
 						if (tid == 0) {
-							if (final_) hdr_publish(gs, wn, r1 + S.nsel, S.pm, true);
+							if (final_) hdr_publish(&gs->hdr[wn & 1], wn, r1 + S.nsel, S.pm, true);
 							__threadfence();
 							st_release_gpu(final_ ? &gs->sel_flag : &gs->need_full, (unsigned)wn + 1);
 						}
@@ -835,7 +841,7 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 
 		/* ---- after the streaming loop: the panel's geometry is derived AGAIN, from re-read words
 		 * (see PanelGeo), so that the loop above shares no registers with what follows -------- */
-		const uint4 hd2 = ld_volatile_u4(&gs->hdr[w & 1]);
+		const uint4 hd2 = ld_volatile_u4(slow ? &gs->hdr_slow : &gs->hdr[w & 1]);
 		const unsigned lc2 = slow ? *(volatile unsigned *)&gs->list_cnt[w & 1] : 0u;
 		const PanelGeo g2 = panel_geo(M, hd2, lc2, w, G, (int)blockIdx.x);
 		const int wn2 = w + 1;

@@ -62,7 +62,7 @@ def test_resource_usage(lib):
             # must stay free of local-memory traffic -- checked on the SASS in test_forward_sass_shape
             assert int(re.search(r"STACK:(\d+)", body).group(1)) <= 160 and "LOCAL:0" in body, body
             continue
-        if "k_sweepE" in name or "k_sweep_distE" in name:
+        if "k_sweepE" in name or "k_sweep_distE" in name or "k_sweep_applyE" in name:
             # the general (boundary-unit) path of the launch-based sweeps parks one row piece on the
             # stack since the lean loop joined them; the lean loop itself is checked on the SASS
             assert int(re.search(r"STACK:(\d+)", body).group(1)) <= 16 and "LOCAL:0" in body, body
