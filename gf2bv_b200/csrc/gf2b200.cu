@@ -765,11 +765,8 @@ static int forward_single(gf2b200_system *sys, long long *launches) {
 		PanelDesc *pd = h.d_pd + (w & 1), *pdn = (w + 1 < nw && fused) ? h.d_pd + ((w + 1) & 1) : nullptr;
 		u64 colmask_next = ~0ULL;
 		if (w + 1 == nw - 1 && (M.n & 63)) colmask_next = (1ULL << (M.n & 63)) - 1;
-		/* SWEEP_TAIL_SELECT: the previous sweep's last CTA already settled this panel */
-		if (!(SWEEP_TAIL_SELECT && fused && w > 0)) {
-			k_select<<<1, SEL_THREADS, 0, st>>>(M, pc_cur, w, colmask, h.d_state, pd, h.d_hist_r, h.d_hist_pm);
-			(*launches)++;
-		}
+		k_select<<<1, SEL_THREADS, 0, st>>>(M, pc_cur, w, colmask, h.d_state, pd, h.d_hist_r, h.d_hist_pm);
+		(*launches)++;
 		int s0a = w >> SW_SHIFT;
 #if SW == 8
 		if (tail_apply) {

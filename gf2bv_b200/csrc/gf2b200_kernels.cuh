@@ -97,7 +97,7 @@ struct SolverState {
 	long long r_loc; /* first active row of this shard (== r on a single GPU) */
 	int inconsistent;
 	int fault;       /* a peer-memory flag wait timed out */
-	unsigned sweep_done; /* SWEEP_TAIL_SELECT: CTAs of the running sweep that have finished */
+	unsigned sweep_done; /* (unused: the tail-select variant of k_sweep was measured neutral and removed) */
 	/* row-sharded systems (gf2b200_dist.cuh): panel + 1 whose candidates this shard has already
 	 * published / whose election it has already run from inside the previous sweep, and the
 	 * CTA counter of the pivot-row pull */
@@ -553,30 +553,17 @@ k_apply(Mat M, const PanelDesc *__restrict__ pd, uint4 *__restrict__ ebuf, int s
 #endif
 #define SWEEP_RU (SWEEP_THREADS / SQ * SWEEP_U) /* rows per unit */
 #define EBUF_Q (64 * SQ) /* uint4 per strip in ebuf */
-/* Two scheduling switches of k_sweep at a strip change (64-byte strips only: they need
- * the E tile outside the tables).  A/B on one box at n = 131072 (profiles/r01f_ab.txt,
- * r01e_ab.txt): neither 622.6 ms per solve, early tile alone 608.8 ms, both 626 ms --
- * the early tile hides the TMA round trip of ~14 strip changes per CTA and launch, the
- * early loads lengthen the build (registers held across it) by more than they hide. */
-#ifndef SWEEP_PC_SHFL
-/* 1: the coefficient of a row is loaded by one of the SQ threads that share the row and
- * passed on by warp shuffle (the global side of the l1tex pipe costs 12.8 wavefronts per warp
- * where 8 are needed; the SQ-fold coefficient load is 2 of them).  Not yet timed on a GPU. */
-#define SWEEP_PC_SHFL 0
-#endif
-#ifndef SWEEP_UNCOND_LOADS
-/* profiles/r01g_sweep_hotspots.md: ~11 % of the stall samples sit on the coefficient load that
- * gates the row loads; 1 = issue the row loads unconditionally.  Not yet timed on a GPU. */
-#define SWEEP_UNCOND_LOADS 0
-#endif
-#ifndef SWEEP_EARLY_LOADS
-#define SWEEP_EARLY_LOADS 0 /* issue a unit's row loads before the table build of its strip */
-#endif
+/* SWEEP_EARLY_TILE (64-byte strips only: it needs the E tile outside the tables): request the next
+ * strip's E tile (TMA) during the current table build -- hides the TMA round trip of the strip
+ * changes, 622.6 -> 608.8 ms at n = 131072 (profiles/r01f_ab.txt).  Measured and removed (DESIGN.md
+ * section 3, profiles/r02_ab.md call A): one coefficient load per row + warp shuffle (-2 %), row loads not
+ * gated by the coefficient (neutral here; k_forward and the lean unit do it), row loads issued before
+ * the table build (+1 %). */
 #ifndef SWEEP_EARLY_TILE
-#define SWEEP_EARLY_TILE (SW == 8) /* request the next strip's E tile (TMA) during the current build */
+#define SWEEP_EARLY_TILE (SW == 8)
 #endif
-#if (SWEEP_EARLY_LOADS || SWEEP_EARLY_TILE) && SW == 16
-#error "SWEEP_EARLY_LOADS / SWEEP_EARLY_TILE need GF2_STRIP_WORDS=8"
+#if SWEEP_EARLY_TILE && SW == 16
+#error "SWEEP_EARLY_TILE needs GF2_STRIP_WORDS=8"
 #endif
 #if SW == 16
 #define SWEEP_LINES (8 * 128 + 256)
@@ -752,13 +739,6 @@ static_assert(SWEEP_THREADS == 8 * 32 * 4, "one partial-table item per thread; (
 #define SWEEP_SEL_PAD 6 /* units CTA 0 is spared to make room for the fused pivot search (2: 631, 4: 626, 6: 622 ms) */
 #endif
 
-#ifndef SWEEP_TAIL_SELECT
-/* 1: the last CTA of a sweep to finish runs the full pivot scan of the next panel
- * when the fused search did not settle it, and the host stops launching k_select
- * for panels > 0 (a no-op launch of ~2.3 us in almost every panel).  Off until it
- * has been A/B-ed on a GPU; checked against the oracle on the emulated kernels. */
-#define SWEEP_TAIL_SELECT 0
-#endif
 
 /* gpu-scope release / acquire of a flag word (look-ahead verdicts inside a launch, k_forward's barriers) */
 #ifndef GF2_EMU
@@ -972,13 +952,11 @@ sweep_body(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_c
 	for (long long u = u0; u < u1; ++u) {
 		const int s = s0 + (int)(u / nchunks);
 		const long long chunk = u % nchunks;
-#if !SWEEP_EARLY_LOADS
 		enter_strip(s, u);
-#endif
 		const long long row0 = r1 + chunk * SWEEP_RU + rl;
 		const bool force = (s == snext);
 		uint4 *p = mb + ((long long)s * M.mp + row0) * SQ + ch;
-#if SW == 8 && SWEEP_LEAN_UNITS && !SWEEP_EARLY_LOADS
+#if SW == 8 && SWEEP_LEAN_UNITS
 		if (!force && chunk < rows / SWEEP_RU) {
 			/* every consecutive unit of this strip whose SWEEP_RU rows are all active */
 			const long long nl = min(rows / SWEEP_RU - chunk, u1 - u);
@@ -997,30 +975,14 @@ sweep_body(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_c
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {
 			long long row = row0 + (SWEEP_THREADS / SQ) * q;
-#if SWEEP_PC_SHFL
-			/* one lane per row loads the coefficient, its SQ - 1 neighbours get it by shuffle */
-			u64 c = (ch == 0 && row < m) ? (__ldg(pc_cur + row) & pm) : 0;
-			cf[q] = shfl64(c, (tid & 31) & ~(SQ - 1));
-#else
 			cf[q] = (row < m) ? (__ldg(pc_cur + row) & pm) : 0;
-#endif
 		}
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {
 			long long row = row0 + (SWEEP_THREADS / SQ) * q;
 			act[q] = (row < m) && (cf[q] != 0 || force);
-#if SWEEP_UNCOND_LOADS
-			/* do not wait for the coefficient before asking for the row piece: the two
-			 * loads overlap instead of chaining (rows with a zero coefficient -- rare on
-			 * dense systems -- are then read for nothing, never written) */
-			if (row < m) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ);
-#else
 			if (act[q]) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ);
-#endif
 		}
-#if SWEEP_EARLY_LOADS
-		enter_strip(s, u); /* this unit's row pieces are already in flight during the build */
-#endif
 #pragma unroll
 		for (int q = 0; q < SWEEP_U; q++) {
 			if (!act[q]) continue;
@@ -1110,29 +1072,6 @@ k_sweep(Mat M, const PanelDesc *__restrict__ pd, const u64 *__restrict__ pc_cur,
         PanelDesc *pd_next, SolverState *st, long long *hist_r, u64 *hist_pm, u64 colmask_next) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	sweep_body(M, pd, pc_cur, pc_next, ebuf, w, s0, pd_next, st, hist_r, hist_pm, colmask_next);
-#if SWEEP_TAIL_SELECT
-	if (!pd_next) return;
-	__shared__ int is_last;
-	__threadfence(); /* this CTA's pc_next words (and CTA 0's panel description) before its ticket */
-	__syncthreads();
-	if (threadIdx.x == 0) is_last = (atomicAdd(&st->sweep_done, 1u) == gridDim.x - 1);
-	__syncthreads();
-	if (!is_last) return;
-	if (threadIdx.x == 0) st->sweep_done = 0;
-	const int wn = w + 1;
-	if (*(volatile int *)&pd_next->valid == wn + 1) return;
-	/* the fused search saw too few rows (or none ran): scan every active row, as k_select would */
-#if SW == 16
-	SelectSmem &S = *reinterpret_cast<SelectSmem *>(smem_raw);
-#else
-	SelectSmem &S = *reinterpret_cast<SelectSmem *>(smem_raw + SWEEP_LINES * 128);
-#endif
-	const long long r = *(volatile long long *)&st->r;
-	select_init(S);
-	__syncthreads();
-	select_scan(S, pc_next, r, M.m, colmask_next);
-	if (threadIdx.x < 32) select_finalize(S, pc_next, wn, r, st, pd_next, hist_r, hist_pm);
-#endif
 }
 
 /* any active row (i >= rank) with b = 1 makes the system inconsistent

@@ -68,26 +68,14 @@ __device__ __forceinline__ void hdr_publish(uint4 *slot, int w, long long r1, u6
 	__stcg(slot, make_uint4((unsigned)(w + 1) | (window_ok ? 0x80000000u : 0u), (unsigned)r1, (unsigned)pm, (unsigned)(pm >> 32)));
 }
 
-/* How the sweep reads a row's coefficient (the panel word pc_cur[row]):
- *   0  ld.cg (L2 only)
- *   1  plain ld.global (L1-cached).  Safe inside the kernel: the words were written before
- *      the last grid barrier, whose acquire invalidates this SM's L1 (PTX memory model:
- *      weak loads after an acquire observe what happened before the release); never the
- *      non-coherent path (ld.global.nc is outside the model).
- * PERSIST_UNCOND_LOADS 1: the row loads do not wait for the coefficient (rows whose
- * coefficient turns out to be zero are read for nothing and not written). */
-#ifndef PERSIST_CF_LOAD
-#define PERSIST_CF_LOAD 1
-#endif
-/* PERSIST_FIRST_TILE_LDG 1: the FIRST E tile of a panel (needed right after the grid barrier,
- * by all 148 CTAs at once) is read with 256 plain 16-byte ld.cg instead of the proxy fence +
- * bulk copy + mbarrier wait; later tiles keep the prefetching bulk copy. */
-#ifndef PERSIST_FIRST_TILE_LDG
-#define PERSIST_FIRST_TILE_LDG 0
-#endif
-#ifndef PERSIST_UNCOND_LOADS
-#define PERSIST_UNCOND_LOADS 1
-#endif
+/* How the sweep reads a row's coefficient (the panel word pc_cur[row]): a plain ld.global (L1-cached).
+ * Safe inside the kernel: the words were written before the last grid barrier, whose acquire
+ * invalidates this SM's L1 (PTX memory model: weak loads after an acquire observe what happened
+ * before the release); never the non-coherent path (ld.global.nc is outside the model).  The row loads
+ * do not wait for the coefficient (rows whose coefficient turns out to be zero are read for nothing
+ * and not written): gating them chained two L2 latencies per unit, 600 -> 582 ms.  Measured equal and
+ * removed: ld.cg for the coefficient; the first E tile of a panel by plain loads instead of the bulk
+ * copy (profiles/r02_ab.md call C). */
 /* Developer trace (-DPERSIST_TRACE=1, scripts/trace_forward.py): thread 32 of every CTA (NOT a
  * lane of warp 0: a lone lane stamping there leaves warp 0 divergent and sends the search's
  * warp collectives down their slow BRA.DIV paths -- a 16 us search read 70 us) stamps
@@ -694,12 +682,6 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 				}
 				if (s != cur) {
 					__syncthreads(); /* everyone is done with the previous tables */
-#if PERSIST_FIRST_TILE_LDG
-					if (cur < 0) {
-						if (tid < EBUF_Q) E[tid] = __ldcg(ebuf + (long long)s * EBUF_Q + tid);
-						__syncthreads();
-					} else
-#endif
 					{
 						if (fetched != s && tid == 0) {
 							fence_proxy_async();
@@ -739,22 +721,13 @@ k_forward(Mat M, u64 *pc0, u64 *pc1, uint4 *ebuf0, uint4 *ebuf1, PanelDesc *pd2,
 #pragma unroll
 				for (int q = 0; q < SWEEP_U; q++) {
 					const long long row = row0 + (SWEEP_THREADS / SQ) * q;
-#if PERSIST_CF_LOAD == 0
-					cf[q] = (row >= r1 && row < m) ? (__ldcg(pc_cur + row) & pm) : 0;
-#else
 					cf[q] = (row >= r1 && row < m) ? (ld_weak_u64(pc_cur + row) & pm) : 0;
-#endif
 				}
 #pragma unroll
 				for (int q = 0; q < SWEEP_U; q++) {
 					const long long row = row0 + (SWEEP_THREADS / SQ) * q;
-#if PERSIST_UNCOND_LOADS
 					if (row >= r1 && row < m) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ);
 					act[q] = (row >= r1 && row < m) && (cf[q] != 0 || force);
-#else
-					act[q] = (row >= r1 && row < m) && (cf[q] != 0 || force);
-					if (act[q]) d[q] = __ldcg(p + (long long)(SWEEP_THREADS / SQ) * q * SQ);
-#endif
 				}
 #pragma unroll
 				for (int q = 0; q < SWEEP_U; q++) {
