@@ -26,7 +26,7 @@ sys.path.insert(0, str(ROOT / "tests" / "cpu_emu"))
 
 # the heavy cases stay on the GPU; everything else is the GPU suite verbatim
 SUBSET = ("not 32768 and not mt19937 and not 8192 and not 1025-3000 and not 2000-1500 and not 4099 "
-          "and not 5000 and not 4096 and not 0.001 and not 2100 and not bignull and not full128")
+          "and not 5000 and not 4096 and not 0.001 and not 2100 and not bignull and not full128 and not 9000-4000")
 
 
 @pytest.fixture(scope="module")
