@@ -42,7 +42,7 @@ for r in rows[hi + 1:]:
     a[1] += v
     a[2] = max(a[2], v)
 tot = sum(v[1] for v in agg.values())
-n_sweeps = agg["k_sweep"][0] if "k_sweep" in agg else 0
+n_sweeps = max((agg[k][0] for k in ("k_sweep", "k_sweep_apply") if k in agg), default=0)
 full_step = n_sweeps >= (n + 63) // 64
 lines = [f"# {tag}: ncu launch list of one bench step (n={n}, 1 GPU)" +
          ("" if full_step else f" -- PARTIAL: the first {n_sweeps} of {(n + 63) // 64} panels "
@@ -74,7 +74,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
         "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed", "launch__shared_mem_config_size"]
-md = [f"# {tag}: `ncu --set full --clock-control none` of k_sweep (n={n}, panels {first_panel}..)", "",
+md = [f"# {tag}: `ncu --set full --clock-control none` of the sweep kernel (k_sweep / k_sweep_apply; n={n}, panels {first_panel}..)", "",
       "| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |",
       "|---|---|" + "---|" * len(data)]
 vals = {}
