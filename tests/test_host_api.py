@@ -71,6 +71,32 @@ def test_pack_codec_matches_oracle_restatement():
         assert np.array_equal(B, wantB), cols
 
 
+def test_pack_codec_block_boundaries_and_sparse_rows():
+    """the packer converts 32 digits (960 bits) -> 15 words at a time and skips all-zero blocks: widths around the
+    block and word boundaries, sparse rows (one or two bits anywhere), rows longer than cols"""
+    rnd = random.Random(3)
+    for cols in (959, 960, 961, 1023, 1024, 1025, 1919, 1920, 1921, 2879, 2880, 2881, 4096, 5000, 19968):
+        eqs = []
+        for _ in range(30):
+            kind = rnd.randrange(4)
+            if kind == 0:
+                e = rnd.getrandbits(cols + 1)
+            elif kind == 1:
+                e = (1 << rnd.randrange(cols + 1)) | (1 << rnd.randrange(cols + 1)) | rnd.getrandbits(1)
+            elif kind == 2:
+                e = rnd.getrandbits(cols + 1 + rnd.choice([1, 29, 30, 31, 959, 960, 961]))
+            else:
+                e = rnd.getrandbits(rnd.randrange(1, cols + 2))
+            eqs.append(e * rnd.choice([1, 1, -1]))
+        eqs += [0, 1, (1 << (cols + 1)) - 1, 1 << cols, 1 << (cols + 1), (1 << 960), (1 << 959) | 1, 1 << 961]
+        a, b = _internal._pack_probe(eqs, cols)
+        A = np.frombuffer(a, dtype=np.uint64).reshape(len(eqs), -1)
+        B = np.frombuffer(b, dtype=np.uint64)
+        wantA, wantB = oracle.pack_equations(eqs, cols)
+        assert np.array_equal(A, wantA), cols
+        assert np.array_equal(B, wantB), cols
+
+
 def test_pack_codec_threaded_path():
     """>= 2^21 words: rows are packed by several threads without the GIL (64-row blocks)."""
     rnd = random.Random(2)
