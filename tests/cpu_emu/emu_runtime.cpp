@@ -175,11 +175,39 @@ static void cta_start(size_t ci, unsigned bx, dim3 block, size_t nt, size_t stac
 /* run the fibers of CTA objects [0, n) until all are done */
 static void run_ctas(size_t n, size_t nt) {
 	size_t remaining = n * nt;
+	/* GF2_EMU_STARVE=<seed>: in a cooperative launch one CTA at a time is held back for a burst of 8 - 71
+	 * scheduler rounds -- CTAs drift apart by many rounds, as they do on a GPU under a tool or a debugger.
+	 * The plain round-robin never lets a CTA be "late", which hid an ordering bug of k_forward's slow path
+	 * (profiles/r02_sanitizer.md). */
+	static unsigned long long starve = 0;
+	static bool starve_init = false;
+	if (!starve_init) {
+		const char *e = getenv("GF2_EMU_STARVE");
+		starve = e ? strtoull(e, nullptr, 10) * 2 + 1 : 0;
+		starve_init = true;
+	}
+	size_t victim = 0, burst = 0;
 	while (remaining > 0) {
 		bool progress = false;
+		bool skipped = false;
+		if (starve && n > 1) {
+			if (burst) {
+				burst--;
+			} else {
+				starve = starve * 6364136223846793005ULL + 1442695040888963407ULL;
+				if (((starve >> 40) & 3) == 0) {
+					victim = (size_t)((starve >> 44) % n);
+					burst = 8 + (size_t)((starve >> 52) & 63);
+				}
+			}
+		}
 		for (size_t ci = 0; ci < n; ci++) {
 			Cta &C = *ctas[ci];
 			if (!C.alive) continue;
+			if (burst && ci == victim) {
+				skipped = true;
+				continue;
+			}
 			for (size_t t = 0; t < nt; t++) {
 				Fiber &f = C.f[t];
 				if (f.done || !runnable(f)) continue;
@@ -195,7 +223,7 @@ static void run_ctas(size_t n, size_t nt) {
 				if (f.done) remaining--;
 			}
 		}
-		if (!progress) {
+		if (!progress && !skipped) {
 			fprintf(stderr, "emu: deadlock (%zu threads parked)\n", remaining);
 			abort();
 		}

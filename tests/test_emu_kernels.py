@@ -62,6 +62,23 @@ def test_gpu_parity_suite_on_emulated_kernels(emu_runs, strip_words):
     assert " passed" in tail and "failed" not in tail, tail
 
 
+@pytest.mark.parametrize("forward,seed", [("persist", 1), ("persist", 2), ("launches", 3)])
+def test_flag_protocols_survive_starved_ctas(forward, seed):
+    """GF2_EMU_STARVE: the emulator's scheduler holds one CTA at a time back for 8 - 71 rounds of a
+    cooperative launch.  k_forward (slow path, look-ahead, list sweep) and k_sweep_apply hand data over
+    between CTAs through release / acquire flags; a protocol that silently relies on the CTAs arriving
+    together -- as the slow path's header did before `GridSync::hdr_slow` (profiles/r02_sanitizer.md: found on the
+    GPU under compute-sanitizer, reproduced by this knob) -- ends in a timed-out wait here."""
+    import build_emu
+
+    lib = build_emu.build(8)
+    env = dict(os.environ, GF2B200_LIB=str(lib), GF2_EMU_SMS="4", GF2B200_TEST_EMULATION="1",
+               GF2_EMU_STARVE=str(seed), GF2B200_FORWARD=forward)
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "cpu_emu" / "starve_probe.py")], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0 and "starve probe ok" in r.stdout, (r.stdout + r.stderr)[-800:]
+
+
 def test_emulated_library_is_not_the_product():
     """the package never points at the emulated build by itself, and refuses it when pointed
     at it without the tests' explicit switch (ctypes shim and CPython extension alike)"""
